@@ -1,0 +1,870 @@
+// snb_api.cu -- host side of libsnb200.so: the C ABI of include/snb.h over the CUDA runtime.
+//
+// Mirrors the chunk drivers of the reference (snappy.nim:27-64 compress, :84-110 uncompress,
+// :130-155 compressFramed, :169-267 uncompressFramed; bounds of snappy/codec.nim) and hands the
+// per-chunk work (encodeFrame / encodeBlock / uncompress / maskedCrc) to the kernels in
+// snb_device.cuh.  There is no CPU implementation of that work in this library: without a
+// CUDA device every data-path call returns SNB_CUDA_ERROR.
+#include "../../include/snb.h"
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#ifdef SNB_EMULATE
+#include "cuda_emu.h"
+#include "cuda_rt_emu.h"
+#define SNB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#define SNB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(unsigned)(grid), (unsigned)(block), (size_t)(smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
+#include "snb_device.cuh"
+
+static_assert(sizeof(snb_chunk) == sizeof(snb::Chunk), "snb_chunk must match the device descriptor");
+
+namespace {
+
+constexpr uint64_t kChunk = snb::kMaxBlock;
+constexpr uint64_t kFrameStride = 65664;           // >= 65544 (stored frame) and >= the abort bound, multiple of 128
+constexpr uint64_t kRawStride = 76544;             // >= maxCompressedLen(65536) = 76490, multiple of 128
+constexpr uint32_t kDevSlabChunks = 16384;         // 1 GiB of input per device-side slab
+constexpr uint32_t kHostSlabChunks = 1024;         // 64 MiB of input per host<->device slab
+constexpr int kNumCounters = 256;
+const uint8_t kStreamHeader[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};  // codec.nim:33-34
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return (T*)p; }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, n + 256);
+    if (e == cudaSuccess) cap = n + 256;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return (T*)p; }
+};
+
+struct Ctx {
+  bool ready = false;
+  int device = 0, sms = 148;
+  cudaStream_t s0 = nullptr, s_in = nullptr, s_out = nullptr;
+  snb::CrcTables h_tables;
+  snb::CrcTables* d_tables = nullptr;
+  uint8_t* d_hdr = nullptr;
+  uint32_t* d_counters = nullptr;
+  int counter_next = 0;
+  uint64_t* d_total = nullptr;  // 4 device scalars
+  DevBuf scratch, lens, offs, crcs, chunks, status, outlen, in[2], out[2];
+  PinBuf h_in[2], h_out[2], h_meta[2];
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t ev_prof[12] = {};
+  bool profiling = false;
+  float prof[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t launches = 0;
+  uint32_t call_launches = 0;
+  int compress_warps = 6;
+  std::string err;
+};
+Ctx g;
+std::mutex g_mu;
+
+int fail(const char* what, cudaError_t e) {
+  g.err = std::string(what) + ": " + cudaGetErrorString(e);
+  return SNB_CUDA_ERROR;
+}
+#define CK(x)                                             \
+  do {                                                    \
+    cudaError_t e_ = (x);                                 \
+    if (e_ != cudaSuccess) return fail(#x, e_);           \
+  } while (0)
+#define CKS(x)                                            \
+  do {                                                    \
+    int s_ = (x);                                         \
+    if (s_ != SNB_OK) return s_;                          \
+  } while (0)
+
+// ---------------------------------------------------------------- GF(2) helpers (host: table construction + CRC combine)
+uint32_t h_mulmod(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+  for (int i = 0; i < 32; i++) {
+    if (a & 0x80000000u) p ^= b;
+    a <<= 1;
+    b = (b >> 1) ^ ((b & 1u) ? snb::kCrcPoly : 0u);
+  }
+  return p;
+}
+uint32_t h_pow(uint32_t a, uint64_t e) {
+  uint32_t r = 0x80000000u;
+  while (e) {
+    if (e & 1) r = h_mulmod(r, a);
+    a = h_mulmod(a, a);
+    e >>= 1;
+  }
+  return r;
+}
+void build_tables(snb::CrcTables& t) {
+  for (uint32_t i = 0; i < 256; i++) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? snb::kCrcPoly : 0);
+    t.byte[i] = c;
+  }
+  const uint32_t x8 = 0x00800000u;  // x^8
+  t.x8[0] = 0x80000000u;
+  for (int k = 1; k < 512; k++) t.x8[k] = h_mulmod(t.x8[k - 1], x8);
+  const uint32_t x4096 = h_mulmod(t.x8[511], x8);
+  t.xn[0] = 0x80000000u;
+  for (int q = 1; q < 132; q++) t.xn[q] = h_mulmod(t.xn[q - 1], x4096);
+  const uint32_t xinv = (snb::kCrcPoly << 1) | 1u;  // x^-1 = (P - 1) / x
+  const uint32_t xm128 = h_pow(xinv, 128);
+  t.ainv[0] = 0x80000000u;
+  for (int l = 1; l < 32; l++) t.ainv[l] = h_mulmod(t.ainv[l - 1], xm128);
+  for (int j = 0; j < 16; j++)
+    for (int b = 0; b < 256; b++) t.row[j][b] = h_mulmod(t.byte[b], t.x8[511 - j]);
+}
+// CRC(A || B) from the finalised CRCs of A and B.
+uint32_t crc_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) {
+  return h_mulmod(h_pow(0x00800000u, len_b), crc_a) ^ crc_b;
+}
+
+// ---------------------------------------------------------------- varints (stew/leb128 semantics)
+int put_varint32(uint8_t* o, uint32_t v) {
+  int n = 0;
+  while (v >= 0x80) { o[n++] = (uint8_t)(v | 0x80); v >>= 7; }
+  o[n++] = (uint8_t)v;
+  return n;
+}
+// bytes consumed (>0), 0 = truncated, -1 = overflow
+int get_varint(const uint8_t* p, size_t n, int bits, uint64_t* out) {
+  uint64_t v = 0;
+  int max_bytes = (bits + 6) / 7;
+  for (int i = 0; i < max_bytes; i++) {
+    if ((size_t)i >= n) return 0;
+    uint64_t b = p[i];
+    int shift = 7 * i;
+    if (i == max_bytes - 1) {
+      if (b & 0x80) return -1;
+      if (bits - shift < 7 && (b >> (bits - shift)) != 0) return -1;
+    }
+    v |= (b & 0x7f) << shift;
+    if (!(b & 0x80)) { *out = v; return i + 1; }
+  }
+  return -1;
+}
+inline uint32_t le32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// ---------------------------------------------------------------- init
+int do_init(int device) {
+  if (g.ready) {
+    if (device >= 0 && device != g.device) { g.err = "snb_init: already bound to another device (one process per GPU)"; return SNB_CUDA_ERROR; }
+    return SNB_OK;
+  }
+  if (device < 0) device = 0;
+  CK(cudaSetDevice(device));
+  g.device = device;
+  CK(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, device));
+  CK(cudaStreamCreateWithFlags(&g.s0, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g.s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaEventCreateWithFlags(&g.ev_h2d[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_comp[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_d2h[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < 12; i++) CK(cudaEventCreate(&g.ev_prof[i]));
+  build_tables(g.h_tables);
+  CK(cudaMalloc((void**)&g.d_tables, sizeof(snb::CrcTables)));
+  CK(cudaMemcpy(g.d_tables, &g.h_tables, sizeof(snb::CrcTables), cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&g.d_hdr, 16));
+  CK(cudaMemcpy(g.d_hdr, kStreamHeader, 10, cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&g.d_counters, kNumCounters * sizeof(uint32_t)));
+  CK(cudaMalloc((void**)&g.d_total, 4 * sizeof(uint64_t)));
+  CK(cudaFuncSetAttribute(snb::compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  g.ready = true;
+  return SNB_OK;
+}
+int need_init() { return g.ready ? SNB_OK : do_init(-1); }
+
+// A zeroed work-queue counter for one persistent launch.
+int next_counter(cudaStream_t st, uint32_t** out) {
+  uint32_t* c = g.d_counters + (g.counter_next++ % kNumCounters);
+  CK(cudaMemsetAsync(c, 0, sizeof(uint32_t), st));
+  *out = c;
+  return SNB_OK;
+}
+void count_launch() { g.launches++; g.call_launches++; }
+void prof_mark(int i, cudaStream_t st) { if (g.profiling) cudaEventRecord(g.ev_prof[i], st); }
+void prof_begin() { g.call_launches = 0; }
+void prof_collect(int first_pair, int n_pairs, int slot0) {
+  // caller has synchronised the stream
+  if (!g.profiling) return;
+  for (int i = 0; i < n_pairs; i++) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev_prof[first_pair + 2 * i], g.ev_prof[first_pair + 2 * i + 1]);
+    g.prof[slot0 + i] += ms;
+  }
+}
+
+// ---------------------------------------------------------------- launch geometry
+struct CompressGeom { uint32_t entries, warps, grid; size_t smem; };
+CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
+  CompressGeom cg;
+  uint32_t e = 256;
+  while (e < snb::kMaxTableEntries && e < max_len) e <<= 1;
+  cg.entries = e;
+  size_t tbytes = (size_t)e * 2;
+  uint32_t ctas_per_sm;
+  if (e == snb::kMaxTableEntries) {
+    cg.warps = (uint32_t)std::max(1, std::min(7, g.compress_warps));
+    ctas_per_sm = 1;
+  } else {
+    cg.warps = 8;
+    ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (cg.warps * tbytes + 1024)));
+  }
+  cg.smem = cg.warps * tbytes;
+  uint32_t need = (count + cg.warps - 1) / cg.warps;
+  cg.grid = std::max(1u, std::min(need, (uint32_t)g.sms * ctas_per_sm));
+  return cg;
+}
+
+// ---------------------------------------------------------------- device-side building blocks
+int launch_crc(const uint8_t* base, const uint64_t* off, const uint32_t* len, uint64_t total_len, uint32_t count,
+               uint32_t* out, uint32_t masked, cudaStream_t st) {
+  if (!count) return SNB_OK;
+  snb::CrcArgs a;
+  a.base = base; a.off = off; a.len = len; a.total_len = total_len; a.out = out; a.count = count; a.masked = masked;
+  uint32_t grid = std::max(1u, std::min((count + 7) / 8, (uint32_t)g.sms * 8));
+  SNB_LAUNCH(snb::crc_kernel, grid, 256, 0, st, a, g.d_tables);
+  count_launch();
+  CK(cudaGetLastError());
+  return SNB_OK;
+}
+
+// Compress the 64 KiB blocks of a contiguous device buffer and pack the results back to back
+// at d_dst + dst_base.  mode: kModeFrame (encodeFrame per block) or kModeRawBlock.
+// d_total[0] receives the end offset (dst_base + bytes produced).
+int dev_compress_contig(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t* d_dst, uint64_t dst_base,
+                        uint32_t* d_frame_lens, cudaStream_t st) {
+  uint64_t count64 = (n + kChunk - 1) / kChunk;
+  if (count64 == 0) {
+    CK(cudaMemcpyAsync(g.d_total, &dst_base, 8, cudaMemcpyHostToDevice, st));
+    return SNB_OK;
+  }
+  uint32_t slab = (uint32_t)std::min<uint64_t>(count64, kDevSlabChunks);
+  const uint64_t kSlotStride = mode == snb::kModeFrame ? kFrameStride : kRawStride;
+  CK(g.scratch.ensure((size_t)slab * kSlotStride + 4096));
+  CK(g.lens.ensure((size_t)slab * 4));
+  CK(g.offs.ensure((size_t)slab * 8));
+  CK(g.crcs.ensure((size_t)slab * 4));
+  for (uint64_t first = 0; first < count64; first += slab) {
+    uint32_t cnt = (uint32_t)std::min<uint64_t>(slab, count64 - first);
+    const uint8_t* sin = d_in + first * kChunk;
+    uint64_t slen = std::min<uint64_t>(n - first * kChunk, (uint64_t)cnt * kChunk);
+    bool p = g.profiling && first == 0;
+    if (mode == snb::kModeFrame) {
+      if (p) prof_mark(0, st);
+      CKS(launch_crc(sin, nullptr, nullptr, slen, cnt, g.crcs.as<uint32_t>(), 1, st));
+      if (p) prof_mark(1, st);
+    }
+    snb::CompressArgs a;
+    a.in_base = sin; a.out_base = g.scratch.as<uint8_t>(); a.in_off = nullptr; a.in_len = nullptr; a.out_off = nullptr;
+    a.total_len = slen; a.out_stride = kSlotStride; a.crc = g.crcs.as<uint32_t>(); a.out_len = g.lens.as<uint32_t>();
+    a.count = cnt; a.mode = mode;
+    CKS(next_counter(st, &a.counter));
+    CompressGeom cg = compress_geom((uint32_t)kChunk, cnt);
+    a.table_entries = cg.entries;
+    if (p) prof_mark(2, st);
+    SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
+    count_launch();
+    CK(cudaGetLastError());
+    if (p) { prof_mark(3, st); prof_mark(4, st); }
+    SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, st, g.lens.as<uint32_t>(), g.offs.as<uint64_t>(), cnt,
+               first == 0 ? (const uint64_t*)nullptr : (const uint64_t*)g.d_total, first == 0 ? dst_base : 0ull,
+               g.d_total);
+    count_launch();
+    CK(cudaGetLastError());
+    if (p) { prof_mark(5, st); prof_mark(6, st); }
+    uint32_t cgrid = std::max(1u, std::min(cnt, (uint32_t)g.sms * 8));
+    SNB_LAUNCH(snb::compact_kernel, cgrid, 256, 0, st, g.scratch.as<uint8_t>(), kSlotStride, g.lens.as<uint32_t>(),
+               g.offs.as<uint64_t>(), d_dst, cnt);
+    count_launch();
+    CK(cudaGetLastError());
+    if (p) prof_mark(7, st);
+    if (d_frame_lens)
+      CK(cudaMemcpyAsync(d_frame_lens + first, g.lens.p, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return SNB_OK;
+}
+
+int launch_decompress(const uint8_t* d_in, uint8_t* d_out, const snb::Chunk* d_chunks, uint32_t count, int verify,
+                      int32_t* d_status, uint32_t* d_outlen, cudaStream_t st) {
+  if (!count) return SNB_OK;
+  snb::DecompressArgs a;
+  a.in_base = d_in; a.out_base = d_out; a.chunks = d_chunks; a.status = d_status; a.out_len = d_outlen;
+  a.count = count; a.verify = verify ? 1u : 0u;
+  CKS(next_counter(st, &a.counter));
+  uint32_t grid = std::max(1u, std::min((count + 7) / 8, (uint32_t)g.sms * 8));
+  prof_mark(8, st);
+  SNB_LAUNCH(snb::decompress_kernel, grid, 256, 0, st, a, g.d_tables);
+  count_launch();
+  CK(cudaGetLastError());
+  prof_mark(9, st);
+  return SNB_OK;
+}
+
+bool is_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// ---------------------------------------------------------------- host-buffer compress pipeline
+// Streams `n` input bytes through the GPU in slabs: H2D (s_in) | kernels (s0) | D2H (s_out),
+// double buffered.  The packed output of slab k lands at out + *pos.
+int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, uint32_t mode) {
+  if (n == 0) return SNB_OK;
+  const uint64_t slab_bytes = (uint64_t)kHostSlabChunks * kChunk;
+  const uint64_t nslab = (n + slab_bytes - 1) / slab_bytes;
+  const size_t per_block = mode == snb::kModeFrame ? (size_t)(kChunk + 8) : (size_t)SNB_MAX_COMPRESSED_FRAME_LEN;
+  const size_t out_slab_cap = (size_t)kHostSlabChunks * per_block + 65536;
+  const bool pin_in = is_pinned(in), pin_out = is_pinned(out);
+  const size_t in_cap = (size_t)std::min<uint64_t>(n, slab_bytes);
+  const int nbuf = nslab > 1 ? 2 : 1;
+  for (int i = 0; i < nbuf; i++) {
+    CK(g.in[i].ensure(in_cap + 64));
+    CK(g.out[i].ensure(nslab > 1 ? out_slab_cap : (size_t)((n + kChunk - 1) / kChunk) * per_block + 65536));
+    if (!pin_in) CK(g.h_in[i].ensure(in_cap));
+    if (!pin_out) CK(g.h_out[i].ensure(g.out[i].cap));
+    CK(g.h_meta[i].ensure(64));
+  }
+  uint64_t slab_len[2] = {0, 0};
+  auto finish = [&](uint64_t k) -> int {
+    int s = (int)(k & 1);
+    CK(cudaEventSynchronize(g.ev_comp[s]));
+    uint64_t total = *g.h_meta[s].as<uint64_t>();
+    if (pin_out) {
+      CK(cudaMemcpyAsync(out + *pos, g.out[s].p, total, cudaMemcpyDeviceToHost, g.s_out));
+      CK(cudaEventRecord(g.ev_d2h[s], g.s_out));
+    } else {
+      CK(cudaMemcpyAsync(g.h_out[s].p, g.out[s].p, total, cudaMemcpyDeviceToHost, g.s_out));
+      CK(cudaStreamSynchronize(g.s_out));
+      memcpy(out + *pos, g.h_out[s].p, total);
+      CK(cudaEventRecord(g.ev_d2h[s], g.s_out));
+    }
+    *pos += total;
+    return SNB_OK;
+  };
+  for (uint64_t k = 0; k < nslab; k++) {
+    int s = (int)(k & 1);
+    uint64_t off = k * slab_bytes, len = std::min<uint64_t>(slab_bytes, n - off);
+    slab_len[s] = len;
+    if (k >= 2) CK(cudaStreamWaitEvent(g.s_in, g.ev_comp[s], 0));  // d_in[s] consumed by slab k-2
+    if (pin_in) {
+      CK(cudaMemcpyAsync(g.in[s].p, in + off, len, cudaMemcpyHostToDevice, g.s_in));
+    } else {
+      if (k >= 2) CK(cudaEventSynchronize(g.ev_h2d[s]));  // staging buffer free again
+      memcpy(g.h_in[s].p, in + off, len);
+      CK(cudaMemcpyAsync(g.in[s].p, g.h_in[s].p, len, cudaMemcpyHostToDevice, g.s_in));
+    }
+    CK(cudaEventRecord(g.ev_h2d[s], g.s_in));
+    CK(cudaStreamWaitEvent(g.s0, g.ev_h2d[s], 0));
+    if (k >= 2) CK(cudaStreamWaitEvent(g.s0, g.ev_d2h[s], 0));  // d_out[s] drained by slab k-2
+    CKS(dev_compress_contig(g.in[s].as<uint8_t>(), len, mode, g.out[s].as<uint8_t>(), 0, nullptr, g.s0));
+    CK(cudaMemcpyAsync(g.h_meta[s].p, g.d_total, 8, cudaMemcpyDeviceToHost, g.s0));
+    CK(cudaEventRecord(g.ev_comp[s], g.s0));
+    if (k >= 1) CKS(finish(k - 1));
+  }
+  CKS(finish(nslab - 1));
+  CK(cudaStreamSynchronize(g.s_out));
+  (void)slab_len;
+  return SNB_OK;
+}
+
+// ---------------------------------------------------------------- framed header walk (snappy.nim:186-267)
+struct WalkOut {
+  std::vector<snb_chunk> chunks;
+  snb_walk w;
+};
+void walk_framed(const uint8_t* in, size_t n, size_t cap, int check_header, int check_integrity, WalkOut& o) {
+  memset(&o.w, 0, sizeof o.w);
+  size_t rd = 0, wr = 0;
+  auto stop = [&](int status) { o.w.status = status; o.w.read = rd; o.w.written = wr; };
+  if (check_header) {
+    if (n < 10 || memcmp(in, kStreamHeader, 10) != 0) return stop(SNB_INVALID_INPUT);  // :187-194
+    rd = 10;
+  }
+  while (rd < n) {
+    size_t remaining = n - rd;
+    if (remaining < 4) return stop(SNB_INVALID_INPUT);           // :200-201
+    uint32_t hdr = le32(in + rd);
+    uint8_t id = (uint8_t)hdr;
+    size_t dlen = hdr >> 8;
+    rd += 4;
+    if (remaining - 4 < dlen) return stop(SNB_INVALID_INPUT);    // :206-207
+    if (id == 0x00) {
+      if (dlen < 4) return stop(SNB_INVALID_INPUT);              // :210-211
+      uint64_t ulen = 0;
+      int br = get_varint(in + rd + 4, dlen - 4, 32, &ulen);
+      if (br <= 0) return stop(SNB_INVALID_INPUT);               // snappy.nim:92-94 via :216-228
+      size_t room = std::min<size_t>(kChunk, cap - wr);
+      if (ulen > room) {                                         // :219-229
+        if (ulen > kChunk) return stop(SNB_INVALID_INPUT);
+        o.w.partial = 1; o.w.read = rd - 4; o.w.written = wr;
+        return;
+      }
+      snb_chunk c;
+      c.in_off = rd + 4; c.out_off = wr; c.in_len = (uint32_t)(dlen - 4); c.out_cap = (uint32_t)ulen;
+      c.crc = le32(in + rd); c.kind = snb::kKindCompressed;
+      o.chunks.push_back(c);
+      wr += ulen;
+    } else if (id == 0x01) {
+      if (dlen < 4) return stop(SNB_INVALID_INPUT);              // :238-239
+      size_t ul = dlen - 4;
+      snb_chunk c;
+      c.in_off = rd + 4; c.out_off = wr; c.in_len = (uint32_t)ul; c.out_cap = (uint32_t)ul;
+      c.crc = le32(in + rd); c.kind = snb::kKindStored;
+      if (ul > kChunk) {                                         // :244-251: CRC is checked before the length
+        if (check_integrity) { o.w.big_crc_off = rd + 4; o.w.big_crc_len = ul; o.w.big_crc = c.crc; }
+        return stop(SNB_INVALID_INPUT);
+      }
+      if (ul > cap - wr) {                                       // :253-254, after the CRC check of :244-246
+        if (check_integrity) { c.kind = snb::kKindVerifyOnly; o.chunks.push_back(c); o.w.crc_first = 1; }
+        o.w.partial = 1; o.w.read = rd - 4; o.w.written = wr;
+        return;
+      }
+      o.chunks.push_back(c);
+      wr += ul;
+    } else if (id < 0x80) {
+      return stop(SNB_UNKNOWN_CHUNK);                            // :259-260
+    }                                                            // :262-263 skippable
+    rd += dlen;
+  }
+  o.w.read = rd; o.w.written = wr;
+}
+
+// Plain (finalised, unmasked) CRC-32C of an arbitrary host range, pieces on the GPU, combine on host.
+int host_crc(const uint8_t* buf, size_t n, uint32_t* crc_out) {
+  uint32_t crc = 0;
+  const size_t slab = (size_t)kHostSlabChunks * kChunk;
+  for (size_t off = 0; off < n; off += slab) {
+    size_t len = std::min(slab, n - off);
+    uint32_t cnt = (uint32_t)((len + kChunk - 1) / kChunk);
+    CK(g.in[0].ensure(len + 64));
+    CK(g.crcs.ensure((size_t)cnt * 4));
+    CK(g.h_meta[0].ensure((size_t)cnt * 4));
+    CK(cudaMemcpyAsync(g.in[0].p, buf + off, len, cudaMemcpyHostToDevice, g.s0));
+    CKS(launch_crc(g.in[0].as<uint8_t>(), nullptr, nullptr, len, cnt, g.crcs.as<uint32_t>(), 0, g.s0));
+    CK(cudaMemcpyAsync(g.h_meta[0].p, g.crcs.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, g.s0));
+    CK(cudaStreamSynchronize(g.s0));
+    const uint32_t* pc = g.h_meta[0].as<uint32_t>();
+    for (uint32_t i = 0; i < cnt; i++) {
+      size_t plen = std::min<size_t>(kChunk, len - (size_t)i * kChunk);
+      crc = (off == 0 && i == 0) ? pc[0] : crc_combine(crc, pc[i], plen);
+    }
+  }
+  *crc_out = crc;
+  return SNB_OK;
+}
+inline uint32_t mask_crc(uint32_t c) { return ((c >> 15) | (c << 17)) + snb::kCrcMaskDelta; }
+
+// Decode the walked chunks: slabs of chunks bounded by device buffer sizes, H2D | kernel | D2H.
+// first_bad receives the index of the first chunk with a non-zero status (or -1).
+int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_t* out, int verify,
+                       int64_t* first_bad, int32_t* bad_status) {
+  *first_bad = -1;
+  const size_t count = chunks.size();
+  if (!count) return SNB_OK;
+  const bool pin_in = is_pinned(in), pin_out = is_pinned(out);
+  const uint64_t in_budget = (uint64_t)kHostSlabChunks * kChunk + 2 * SNB_MAX_COMPRESSED_FRAME_LEN;
+  size_t i = 0;
+  uint64_t k = 0;
+  struct Pending { size_t first, cnt; uint64_t out_begin, out_len; };
+  Pending pend[2];
+  auto finish = [&](uint64_t kk) -> int {
+    int s = (int)(kk & 1);
+    Pending& p = pend[s];
+    CK(cudaEventSynchronize(g.ev_d2h[s]));
+    if (!pin_out && p.out_len) memcpy(out + p.out_begin, g.h_out[s].p, p.out_len);
+    const int32_t* st = (const int32_t*)(g.h_meta[s].as<uint8_t>() + p.cnt * sizeof(snb_chunk));
+    for (size_t j = 0; j < p.cnt && *first_bad < 0; j++)
+      if (st[j] != 0) { *first_bad = (int64_t)(p.first + j); *bad_status = st[j]; }
+    return SNB_OK;
+  };
+  while (i < count && *first_bad < 0) {
+    // slab = chunks [i, j): contiguous input range within budget, at most kHostSlabChunks chunks
+    size_t j = i;
+    uint64_t in_begin = chunks[i].in_off, in_end = in_begin, out_begin = chunks[i].out_off, out_end = out_begin;
+    while (j < count && j - i < kHostSlabChunks) {
+      uint64_t e = chunks[j].in_off + chunks[j].in_len;
+      if (j > i && e - in_begin > in_budget) break;
+      in_end = e;
+      if (chunks[j].kind != snb::kKindVerifyOnly) out_end = chunks[j].out_off + chunks[j].out_cap;
+      j++;
+    }
+    int s = (int)(k & 1);
+    size_t cnt = j - i;
+    uint64_t in_len = in_end - in_begin, out_len = out_end - out_begin;
+    if (k >= 2) CKS(finish(k - 2));  // frees slot s (host staging + meta)
+    CK(g.in[s].ensure(in_len + 64));
+    CK(g.out[s].ensure(out_len + 64));
+    CK(g.chunks.ensure(2 * kHostSlabChunks * sizeof(snb_chunk)));
+    CK(g.status.ensure(2 * kHostSlabChunks * 4));
+    CK(g.outlen.ensure(2 * kHostSlabChunks * 4));
+    CK(g.h_meta[s].ensure(cnt * (sizeof(snb_chunk) + 4)));
+    if (!pin_in) CK(g.h_in[s].ensure(in_len));
+    if (!pin_out) CK(g.h_out[s].ensure(out_len));
+    snb_chunk* hm = g.h_meta[s].as<snb_chunk>();
+    for (size_t t = 0; t < cnt; t++) {
+      hm[t] = chunks[i + t];
+      hm[t].in_off -= in_begin;
+      hm[t].out_off -= out_begin;
+    }
+    snb::Chunk* d_chunks = g.chunks.as<snb::Chunk>() + (size_t)s * kHostSlabChunks;
+    int32_t* d_status = g.status.as<int32_t>() + (size_t)s * kHostSlabChunks;
+    uint32_t* d_outlen = g.outlen.as<uint32_t>() + (size_t)s * kHostSlabChunks;
+    if (pin_in) {
+      CK(cudaMemcpyAsync(g.in[s].p, in + in_begin, in_len, cudaMemcpyHostToDevice, g.s_in));
+    } else {
+      memcpy(g.h_in[s].p, in + in_begin, in_len);
+      CK(cudaMemcpyAsync(g.in[s].p, g.h_in[s].p, in_len, cudaMemcpyHostToDevice, g.s_in));
+    }
+    CK(cudaMemcpyAsync(d_chunks, hm, cnt * sizeof(snb_chunk), cudaMemcpyHostToDevice, g.s_in));
+    CK(cudaEventRecord(g.ev_h2d[s], g.s_in));
+    CK(cudaStreamWaitEvent(g.s0, g.ev_h2d[s], 0));
+    CKS(launch_decompress(g.in[s].as<uint8_t>(), g.out[s].as<uint8_t>(), d_chunks, (uint32_t)cnt, verify, d_status,
+                          d_outlen, g.s0));
+    CK(cudaEventRecord(g.ev_comp[s], g.s0));
+    CK(cudaStreamWaitEvent(g.s_out, g.ev_comp[s], 0));
+    if (out_len) {
+      CK(cudaMemcpyAsync(pin_out ? (void*)(out + out_begin) : g.h_out[s].p, g.out[s].p, out_len,
+                         cudaMemcpyDeviceToHost, g.s_out));
+    }
+    CK(cudaMemcpyAsync(g.h_meta[s].as<uint8_t>() + cnt * sizeof(snb_chunk), d_status, cnt * 4, cudaMemcpyDeviceToHost,
+                       g.s_out));
+    CK(cudaEventRecord(g.ev_d2h[s], g.s_out));
+    pend[s] = Pending{i, cnt, out_begin, out_len};
+    i = j;
+    k++;
+    // the next slab reuses the other slot: its previous occupant (k-2) is finished at the loop top
+  }
+  if (k >= 2) CKS(finish(k - 2));
+  if (k >= 1) CKS(finish(k - 1));
+  CK(cudaStreamSynchronize(g.s_in));
+  CK(cudaStreamSynchronize(g.s0));
+  CK(cudaStreamSynchronize(g.s_out));
+  return SNB_OK;
+}
+
+}  // namespace
+
+// ======================================================================== C ABI
+extern "C" {
+
+int snb_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return do_init(device);
+}
+void snb_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g.ready) return;
+  cudaDeviceSynchronize();
+  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.in[0], &g.in[1], &g.out[0], &g.out[1]})
+    b->release();
+  for (PinBuf* b : {&g.h_in[0], &g.h_in[1], &g.h_out[0], &g.h_out[1], &g.h_meta[0], &g.h_meta[1]}) b->release();
+  cudaFree(g.d_tables); cudaFree(g.d_hdr); cudaFree(g.d_counters); cudaFree(g.d_total);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(g.ev_h2d[i]); cudaEventDestroy(g.ev_comp[i]); cudaEventDestroy(g.ev_d2h[i]); }
+  for (int i = 0; i < 12; i++) cudaEventDestroy(g.ev_prof[i]);
+  cudaStreamDestroy(g.s0); cudaStreamDestroy(g.s_in); cudaStreamDestroy(g.s_out);
+  g.ready = false;
+}
+const char* snb_last_error(void) { return g.err.c_str(); }
+
+uint64_t snb_max_compressed_len(uint64_t n) { return 32 + n + n / 6; }
+uint64_t snb_max_compressed_len_framed(int64_t n) {
+  if (n <= 0) return 10;
+  uint64_t frames = ((uint64_t)n + kChunk - 1) / kChunk;
+  return (frames - 1) * (kChunk + 8) + snb_max_compressed_len(kChunk) + 8 + 10;
+}
+int snb_uncompressed_len(const uint8_t* in, size_t n, uint64_t* out) {
+  uint64_t v = 0;
+  if (get_varint(in, n, 64, &v) <= 0) return SNB_INVALID_INPUT;
+  *out = v;
+  return SNB_OK;
+}
+int snb_uncompressed_len_framed(const uint8_t* in, size_t n, uint64_t* out) {  // codec.nim:178-214
+  size_t rd = 0;
+  uint64_t expected = 0;
+  while (rd < n) {
+    size_t remaining = n - rd;
+    if (remaining < 4) return SNB_INVALID_INPUT;
+    uint32_t hdr = le32(in + rd);
+    uint8_t id = (uint8_t)hdr;
+    size_t dlen = hdr >> 8;
+    if (remaining < dlen + 4) return SNB_INVALID_INPUT;
+    rd += 4;
+    uint64_t ul = 0;
+    if (id == 0x00) {
+      if (dlen < 4) return SNB_INVALID_INPUT;
+      if (get_varint(in + rd + 4, dlen - 4, 64, &ul) <= 0) return SNB_INVALID_INPUT;
+    } else if (id == 0x01) {
+      if (dlen < 4) return SNB_INVALID_INPUT;
+      ul = dlen - 4;
+    } else if (id < 0x80) {
+      return SNB_INVALID_INPUT;
+    }
+    if (ul > kChunk) return SNB_INVALID_INPUT;
+    expected += ul;
+    rd += dlen;
+  }
+  *out = expected;
+  return SNB_OK;
+}
+int snb_is_framed_stream(const uint8_t* in, size_t n) { return n >= 10 && memcmp(in, kStreamHeader, 10) == 0; }
+
+int snb_masked_crc32c(const uint8_t* buf, size_t n, uint32_t* crc) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  CKS(need_init());
+  uint32_t c = 0;
+  CKS(host_crc(buf, n, &c));
+  *crc = mask_crc(c);
+  return SNB_OK;
+}
+
+int snb_compress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* written) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if ((uint64_t)n > 0xffffffffull) return SNB_INVALID_INPUT;                // snappy.nim:41-42
+  if ((uint64_t)cap < snb_max_compressed_len(n)) return SNB_BUFFER_TOO_SMALL;  // :44-45
+  CKS(need_init());
+  uint64_t pos = (uint64_t)put_varint32(out, (uint32_t)n);                  // :49-50
+  CKS(host_compress(in, n, out, &pos, snb::kModeRawBlock));
+  *written = (size_t)pos;
+  return SNB_OK;
+}
+
+int snb_compress_framed(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* written) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if ((uint64_t)cap < snb_max_compressed_len_framed((int64_t)n)) return SNB_BUFFER_TOO_SMALL;  // :139-140
+  CKS(need_init());
+  memcpy(out, kStreamHeader, 10);                                            // :142
+  uint64_t pos = 10;
+  CKS(host_compress(in, n, out, &pos, snb::kModeFrame));
+  *written = (size_t)pos;
+  return SNB_OK;
+}
+
+int snb_uncompress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* written) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  *written = 0;
+  CKS(need_init());
+  if ((uint64_t)n > 0xffffffffull) { g.err = "snb_uncompress: input larger than 4 GiB"; return SNB_UNSUPPORTED; }
+  std::vector<snb_chunk> ch(1);
+  ch[0].in_off = 0; ch[0].out_off = 0; ch[0].in_len = (uint32_t)n;
+  ch[0].out_cap = (uint32_t)std::min<uint64_t>(cap, 0xffffffffull);
+  ch[0].crc = 0; ch[0].kind = snb::kKindCompressed;
+  // The device writes at most the announced length; bound the D2H copy by it.
+  uint64_t ulen = 0;
+  int br = get_varint(in, n, 32, &ulen);
+  if (br <= 0) return SNB_INVALID_INPUT;                                     // snappy.nim:92-94
+  if ((uint64_t)cap < ulen) return SNB_BUFFER_TOO_SMALL;                     // :96-97
+  ch[0].out_cap = (uint32_t)ulen;
+  int64_t bad = -1;
+  int32_t bad_status = 0;
+  CKS(host_decode_chunks(in, ch, out, 0, &bad, &bad_status));
+  if (bad >= 0) return bad_status;
+  *written = (size_t)ulen;
+  return SNB_OK;
+}
+
+int snb_frame_index(const uint8_t* stream, size_t n, size_t out_cap, int check_header, int check_integrity,
+                    snb_chunk* chunks, size_t max_chunks, size_t* n_chunks, snb_walk* walk) {
+  WalkOut o;
+  walk_framed(stream, n, out_cap, check_header, check_integrity, o);
+  *n_chunks = o.chunks.size();
+  if (walk) *walk = o.w;
+  if (o.chunks.size() > max_chunks) return SNB_BUFFER_TOO_SMALL;
+  if (!o.chunks.empty()) memcpy(chunks, o.chunks.data(), o.chunks.size() * sizeof(snb_chunk));
+  return SNB_OK;
+}
+
+int snb_uncompress_framed(const uint8_t* in, size_t n, uint8_t* out, size_t cap, int check_header,
+                          int check_integrity, size_t* read, size_t* written) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  *read = 0; *written = 0;
+  WalkOut o;
+  walk_framed(in, n, cap, check_header, check_integrity, o);
+  if (!o.chunks.empty() || o.w.big_crc_len) CKS(need_init());
+  int64_t bad = -1;
+  int32_t bad_status = 0;
+  CKS(host_decode_chunks(in, o.chunks, out, check_integrity, &bad, &bad_status));
+  if (bad >= 0) return bad_status == SNB_CRC_MISMATCH ? SNB_CRC_MISMATCH : SNB_INVALID_INPUT;
+  if (o.w.big_crc_len) {  // oversize stored chunk: crcMismatch outranks invalidInput (snappy.nim:244-251)
+    uint32_t c = 0;
+    CKS(host_crc(in + o.w.big_crc_off, (size_t)o.w.big_crc_len, &c));
+    if (mask_crc(c) != o.w.big_crc) return SNB_CRC_MISMATCH;
+  }
+  if (o.w.status) return o.w.status;
+  *read = (size_t)o.w.read;
+  *written = (size_t)o.w.written;
+  return SNB_OK;
+}
+
+// ---------------------------------------------------------------- device-resident API
+int snb_dev_compress_framed(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, int with_header,
+                            uint32_t* d_frame_lens, uint64_t* d_written, uint64_t* written, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (cap < snb_max_compressed_len_framed((int64_t)n) - (with_header ? 0 : 10)) return SNB_BUFFER_TOO_SMALL;
+  CKS(need_init());
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin();
+  if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
+  uint64_t base = 0;
+  if (with_header) {
+    CK(cudaMemcpyAsync(d_out, g.d_hdr, 10, cudaMemcpyDeviceToDevice, st));
+    base = 10;
+  }
+  if (n == 0) {
+    CK(cudaMemcpyAsync(g.d_total, &base, 8, cudaMemcpyHostToDevice, st));
+  } else {
+    CKS(dev_compress_contig(d_in, n, snb::kModeFrame, d_out, base, d_frame_lens, st));
+  }
+  if (d_written) CK(cudaMemcpyAsync(d_written, g.d_total, 8, cudaMemcpyDeviceToDevice, st));
+  if (written || g.profiling) {
+    CK(g.h_meta[0].ensure(64));
+    CK(cudaMemcpyAsync(g.h_meta[0].p, g.d_total, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (written) *written = *g.h_meta[0].as<uint64_t>();
+    if (n) prof_collect(0, 4, 0);
+    g.prof[5] = (float)g.call_launches;
+  }
+  return SNB_OK;
+}
+
+int snb_dev_uncompress_chunks(const uint8_t* d_in, const snb_chunk* h_chunks, size_t count, uint8_t* d_out,
+                              int check_integrity, int32_t* h_status, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  CKS(need_init());
+  if (!count) return SNB_OK;
+  if (count > 0xffffffffull) return SNB_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin();
+  if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
+  CK(g.chunks.ensure(count * sizeof(snb_chunk)));
+  CK(g.status.ensure(count * 4));
+  CK(g.outlen.ensure(count * 4));
+  CK(cudaMemcpyAsync(g.chunks.p, h_chunks, count * sizeof(snb_chunk), cudaMemcpyHostToDevice, st));
+  CKS(launch_decompress(d_in, d_out, g.chunks.as<snb::Chunk>(), (uint32_t)count, check_integrity,
+                        g.status.as<int32_t>(), g.outlen.as<uint32_t>(), st));
+  CK(cudaMemcpyAsync(h_status, g.status.p, count * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  prof_collect(8, 1, 4);
+  g.prof[5] = (float)g.call_launches;
+  return SNB_OK;
+}
+
+int snb_dev_compress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, size_t count,
+                           uint32_t max_len, uint8_t* d_out, const uint64_t* d_out_off, uint32_t* d_out_len,
+                           void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  CKS(need_init());
+  if (!count) return SNB_OK;
+  if (count > 0xffffffffull) return SNB_UNSUPPORTED;
+  if (max_len == 0 || max_len > kChunk) max_len = (uint32_t)kChunk;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin();
+  if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
+  snb::CompressArgs a;
+  a.in_base = d_in; a.out_base = d_out; a.in_off = d_in_off; a.in_len = d_in_len; a.out_off = d_out_off;
+  a.total_len = 0; a.out_stride = 0; a.crc = nullptr; a.out_len = d_out_len; a.count = (uint32_t)count;
+  a.mode = snb::kModeRawMessage;
+  CKS(next_counter(st, &a.counter));
+  CompressGeom cg = compress_geom(max_len, (uint32_t)count);
+  a.table_entries = cg.entries;
+  prof_mark(2, st);
+  SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
+  count_launch();
+  CK(cudaGetLastError());
+  prof_mark(3, st);
+  if (g.profiling) {
+    CK(cudaStreamSynchronize(st));
+    prof_collect(2, 1, 1);
+    g.prof[5] = (float)g.call_launches;
+  }
+  return SNB_OK;
+}
+
+int snb_dev_uncompress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, size_t count,
+                             uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
+                             uint32_t* d_out_len, int32_t* d_status, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  CKS(need_init());
+  if (!count) return SNB_OK;
+  if (count > 0xffffffffull) return SNB_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin();
+  if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
+  CK(g.chunks.ensure(count * sizeof(snb_chunk)));
+  SNB_LAUNCH(snb::make_chunks_kernel, (count + 255) / 256, 256, 0, st, d_in_off, d_in_len, d_out_off, d_out_cap,
+             g.chunks.as<snb::Chunk>(), (uint32_t)count);
+  count_launch();
+  CK(cudaGetLastError());
+  CKS(launch_decompress(d_in, d_out, g.chunks.as<snb::Chunk>(), (uint32_t)count, 0, d_status, d_out_len, st));
+  if (g.profiling) {
+    CK(cudaStreamSynchronize(st));
+    prof_collect(8, 1, 4);
+    g.prof[5] = (float)g.call_launches;
+  }
+  return SNB_OK;
+}
+
+int snb_dev_uncompressed_lens(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, size_t count,
+                              uint32_t* d_lens, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  CKS(need_init());
+  if (!count) return SNB_OK;
+  SNB_LAUNCH(snb::varint_lens_kernel, (count + 255) / 256, 256, 0, stream, d_in, d_in_off, d_in_len, d_lens,
+             (uint32_t)count);
+  count_launch();
+  CK(cudaGetLastError());
+  return SNB_OK;
+}
+
+int snb_dev_masked_crc32c_chunks(const uint8_t* d_in, uint64_t n, uint32_t* d_crc, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  CKS(need_init());
+  uint64_t count = (n + kChunk - 1) / kChunk;
+  if (count > 0xffffffffull) return SNB_UNSUPPORTED;
+  return launch_crc(d_in, nullptr, nullptr, n, (uint32_t)count, d_crc, 1, (cudaStream_t)stream);
+}
+
+void snb_set_profiling(int enabled) { g.profiling = enabled != 0; }
+int snb_get_profile(float* ms, int n) {
+  int k = std::min(n, 6);
+  for (int i = 0; i < k; i++) ms[i] = g.prof[i];
+  return k;
+}
+uint64_t snb_kernel_launches(void) { return g.launches; }
+void snb_set_compress_warps(int warps) { g.compress_warps = warps; }
+
+}  // extern "C"

@@ -1,0 +1,711 @@
+// snb_device.cuh -- sm_100a device code of the B200-native Snappy codec.
+//
+// One warp owns one block / chunk / message.  All warp collectives are issued convergently
+// with the full mask; "uniform" below means "same value in all 32 lanes".
+//
+// What each routine reproduces (reference file:line, /root/reference @ 8ab5cf0):
+//   crc32c_warp          snappy/crc32c.c:204-214,676-763 + snappy/codec.nim:71-75 (maskedCrc)
+//   compress_block_warp  snappy/encoder.nim:184-383 (encodeBlock), :44-73, :81-125, :130-182
+//   compress_job         snappy/encoder.nim:385-426 (encodeFrame) / snappy.nim:27-64 (compress)
+//   decompress_warp      snappy.nim:84-110 (uncompress) + snappy/decoder.nim:20-155 (decodeAllTags)
+//
+// The file is also compiled by g++ against tests/emu/cuda_emu.h (SNB_EMULATE) so that the
+// warp-level logic is exercised on CPU-only CI; that build is a test double, not a fallback.
+#pragma once
+#include <stdint.h>
+#ifdef SNB_EMULATE
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define SNB_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
+
+namespace snb {
+
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kMaxBlock = 65536;       // codec.nim:14-19
+constexpr uint32_t kInputMargin = 15;       // codec.nim:26
+constexpr uint32_t kMinNonLiteral = 17;     // codec.nim:53
+constexpr uint32_t kMaxTableEntries = 16384;  // encoder.nim:11-12
+constexpr uint32_t kCrcPoly = 0x82F63B78u;  // CRC-32C (Castagnoli), reflected
+constexpr uint32_t kCrcMaskDelta = 0xa282ead8u;
+constexpr uint32_t kNoAbort = 0xffffffffu;
+constexpr uint32_t kAborted = 0xffffffffu;
+constexpr uint32_t kMaxDeviceMessage = 1u << 28;  // per-message bound of the warp decoder
+
+enum : int32_t { kOk = 0, kBufferTooSmall = 1, kInvalidInput = 2, kCrcMismatch = 3, kUnknownChunk = 4, kUnsupported = 101 };
+enum : uint32_t { kModeFrame = 0, kModeRawBlock = 1, kModeRawMessage = 2 };
+enum : uint32_t { kKindCompressed = 0, kKindStored = 1, kKindVerifyOnly = 2 };
+
+__device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+// Unaligned little-endian 32-bit load built from aligned words.  Only words holding at least
+// one requested byte are touched.
+__device__ __forceinline__ uint32_t load32u(const uint8_t* p) {
+  uintptr_t a = (uintptr_t)p;
+  uint32_t sh = (uint32_t)(a & 3) * 8;
+  const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+  uint32_t lo = w[0];
+  uint32_t hi = sh ? w[1] : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+// Up to k (0..4) bytes, zero filled.
+__device__ __forceinline__ uint32_t load_upto4(const uint8_t* p, uint32_t k) {
+  if (k >= 4) return load32u(p);
+  uint32_t v = 0;
+  for (uint32_t i = 0; i < k; i++) v |= (uint32_t)p[i] << (8 * i);
+  return v;
+}
+
+// Cooperative byte copy, any alignment, non-overlapping.  dst-aligned 32-bit stores.
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) {
+  if (n < 64) {
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    return;
+  }
+  uint32_t head = (uint32_t)((0 - (uintptr_t)dst) & 3);
+  if (lane < head) dst[lane] = src[lane];
+  uint32_t words = (n - head) >> 2;
+  uint32_t* dw = (uint32_t*)(dst + head);
+  const uint8_t* s = src + head;
+  if ((((uintptr_t)s) & 3) == 0) {
+    const uint32_t* sw = (const uint32_t*)s;
+    for (uint32_t i = lane; i < words; i += 32) dw[i] = sw[i];
+  } else {
+    for (uint32_t i = lane; i < words; i += 32) dw[i] = load32u(s + 4 * i);
+  }
+  uint32_t done = head + 4 * words;
+  if (lane < n - done) dst[done + lane] = src[done + lane];
+}
+
+// ===================================================================== CRC-32C
+// Tables live in global memory (built on the host once), staged into shared memory per CTA.
+struct CrcTables {
+  uint32_t row[16][256];  // row[j][b] = tab[b] * x^(8*(511-j)): 16 contiguous bytes then a 496-byte skip
+  uint32_t byte[256];     // tab[b]
+  uint32_t x8[512];       // x^(8k)
+  uint32_t xn[132];       // x^(4096q)
+  uint32_t ainv[32];      // x^(-128 L)
+};
+struct CrcSmem {
+  uint32_t row[16][256];
+  uint32_t byte[256];
+};
+
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+#pragma unroll 4
+  for (int i = 0; i < 32; i++) {
+    p ^= (a & 0x80000000u) ? b : 0u;
+    a <<= 1;
+    b = (b >> 1) ^ ((b & 1u) ? kCrcPoly : 0u);
+  }
+  return p;
+}
+__device__ __forceinline__ uint32_t warp_xor(uint32_t v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v ^= __shfl_xor_sync(kFull, v, d);
+  return v;
+}
+__device__ __forceinline__ uint32_t crc_xpow8(const CrcTables* g, uint32_t k) {
+  return crc_mulmod(g->xn[k >> 9], g->x8[k & 511]);
+}
+// F(0, p[0..n)) for n <= 511, lanes take 16-byte pieces.  Uniform result.
+__device__ __forceinline__ uint32_t crc_small(const CrcSmem& t, const CrcTables* g, const uint8_t* p, uint32_t n,
+                                              uint32_t lane) {
+  uint32_t b0 = 16 * lane, c = 0;
+  if (b0 < n) {
+    uint32_t cnt = umin32(16, n - b0);
+    for (uint32_t i = 0; i < cnt; i++) c = t.byte[(c ^ p[b0 + i]) & 0xff] ^ (c >> 8);
+    c = crc_mulmod(c, g->x8[n - b0 - cnt]);
+  }
+  return warp_xor(c);
+}
+// Finalised (~) CRC-32C of p[0..n), n <= 65536 + 15.  Uniform result.
+__device__ __forceinline__ uint32_t crc32c_warp(const CrcSmem& t, const CrcTables* g, const uint8_t* p, uint32_t n,
+                                                uint32_t lane) {
+  uint32_t head = umin32(n, (uint32_t)((0 - (uintptr_t)p) & 15));
+  uint32_t rows = (n - head) >> 9, tail = (n - head) & 511;
+  uint32_t acc = 0;
+  if (head) acc = crc_mulmod(crc_small(t, g, p, head, lane), crc_xpow8(g, n - head));
+  if (rows) {
+    const uint4* q = (const uint4*)(p + head) + lane;
+    uint32_t c = 0;
+    for (uint32_t r = 0; r < rows; r++, q += 32) {
+      uint4 v = *q;
+      v.x ^= c;
+      c = t.row[0][v.x & 0xff] ^ t.row[1][(v.x >> 8) & 0xff] ^ t.row[2][(v.x >> 16) & 0xff] ^ t.row[3][v.x >> 24] ^
+          t.row[4][v.y & 0xff] ^ t.row[5][(v.y >> 8) & 0xff] ^ t.row[6][(v.y >> 16) & 0xff] ^ t.row[7][v.y >> 24] ^
+          t.row[8][v.z & 0xff] ^ t.row[9][(v.z >> 8) & 0xff] ^ t.row[10][(v.z >> 16) & 0xff] ^ t.row[11][v.z >> 24] ^
+          t.row[12][v.w & 0xff] ^ t.row[13][(v.w >> 8) & 0xff] ^ t.row[14][(v.w >> 16) & 0xff] ^ t.row[15][v.w >> 24];
+    }
+    c = warp_xor(crc_mulmod(c, g->ainv[lane]));
+    acc ^= crc_mulmod(c, g->x8[tail]);
+  }
+  if (tail) acc ^= crc_small(t, g, p + head + rows * 512, tail, lane);
+  acc ^= crc_mulmod(0xffffffffu, crc_xpow8(g, n));
+  return ~acc;
+}
+__device__ __forceinline__ uint32_t crc_mask(uint32_t crc) { return ((crc >> 15) | (crc << 17)) + kCrcMaskDelta; }
+
+__device__ __forceinline__ void crc_stage_tables(CrcSmem* s, const CrcTables* g) {
+  const uint32_t* src = &g->row[0][0];
+  uint32_t* dst = &s->row[0][0];
+  for (uint32_t i = threadIdx.x; i < 17 * 256; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+// ===================================================================== compress
+__device__ __forceinline__ uint32_t hash14(uint32_t d, uint32_t mask) {  // encoder.nim:36-37
+  return ((d * 0x1e35a7bdu) >> 18) & mask;
+}
+
+// Length of the common prefix of in[s1..] and in[s2..] (s1 < s2), the s2 side bounded by len.
+// encoder.nim:130-182.  Lane j compares bytes [4j, 4j+4) of each 128-byte step.  Uniform result.
+__device__ __forceinline__ uint32_t common_prefix_warp(const uint8_t* in, uint32_t len, uint32_t s1, uint32_t s2,
+                                                       uint32_t lane) {
+  uint32_t matched = 0;
+  for (;;) {
+    uint32_t o = 4 * lane;
+    uint32_t rem = len - s2;  // bytes left on the s2 side (may be 0)
+    uint32_t nv = rem > o ? umin32(rem - o, 4) : 0;
+    uint32_t x;
+    if (nv == 4) {
+      x = load32u(in + s1 + o) ^ load32u(in + s2 + o);
+    } else {
+      x = 0;
+      for (uint32_t i = 0; i < nv; i++) x |= (uint32_t)(in[s1 + o + i] ^ in[s2 + o + i]) << (8 * i);
+      x |= 1u << (8 * nv);  // sentinel: first byte past the end never matches
+    }
+    uint32_t mism = __ballot_sync(kFull, x != 0);
+    if (mism) {
+      int l = __ffs((int)mism) - 1;
+      uint32_t xl = __shfl_sync(kFull, x, l);
+      return matched + 4 * (uint32_t)l + ((uint32_t)(__ffs((int)xl) - 1) >> 3);
+    }
+    matched += 128; s1 += 128; s2 += 128;
+  }
+}
+
+// Encoded size of an n-byte literal (tag + length bytes + payload), encoder.nim:57-73.
+__device__ __forceinline__ uint32_t literal_size(uint32_t n) { return n + (n <= 60 ? 1 : n <= 256 ? 2 : 3); }
+
+// encoder.nim:44-73.  Returns bytes written (uniform).
+__device__ __forceinline__ uint32_t emit_literal_warp(uint8_t* o, const uint8_t* s, uint32_t n, uint32_t lane) {
+  uint32_t m = (n - 1) & 0xffff, w;
+  if (m < 60) { w = 1; if (lane == 0) o[0] = (uint8_t)(m << 2); }
+  else if (m < 256) { w = 2; if (lane == 0) { o[0] = 60 << 2; o[1] = (uint8_t)m; } }
+  else { w = 3; if (lane == 0) { o[0] = 61 << 2; o[1] = (uint8_t)m; o[2] = (uint8_t)(m >> 8); } }
+  warp_copy(o + w, s, n, lane);
+  return w + n;
+}
+
+// encoder.nim:81-125.  Returns bytes written (uniform).
+__device__ __forceinline__ uint32_t emit_copy_warp(uint8_t* o, uint32_t off, uint32_t len, uint32_t lane) {
+  uint32_t w = 0;
+  if (len >= 68) {  // leading length-64 copies
+    uint32_t q = (len - 68) / 64 + 1;
+    for (uint32_t i = lane; i < q; i += 32) {
+      o[3 * i] = (63 << 2) | 2; o[3 * i + 1] = (uint8_t)off; o[3 * i + 2] = (uint8_t)(off >> 8);
+    }
+    w = 3 * q; len -= 64 * q;
+  }
+  if (len > 64) {
+    if (lane == 0) { o[w] = (59 << 2) | 2; o[w + 1] = (uint8_t)off; o[w + 2] = (uint8_t)(off >> 8); }
+    w += 3; len -= 60;
+  }
+  if (len >= 12 || off >= 2048) {
+    if (lane == 0) { o[w] = (uint8_t)(((len - 1) << 2) | 2); o[w + 1] = (uint8_t)off; o[w + 2] = (uint8_t)(off >> 8); }
+    return w + 3;
+  }
+  if (lane == 0) { o[w] = (uint8_t)(((off >> 8) << 5) | ((len - 4) << 2) | 1); o[w + 1] = (uint8_t)off; }
+  return w + 2;
+}
+
+// encodeBlock (encoder.nim:184-383), one warp, hash table `table` (>= tableSize(len) u16
+// entries of shared memory).  Returns the encoded length, or kAborted as soon as the output
+// exceeds abort_thr (encodeFrame's blockLen <= len - len/8 test, encoder.nim:408, decided early:
+// op only grows).  `out` needs abort_thr + 3100 bytes (frames) or 32+len+len/6 (raw).
+//
+// Literal scan: the probe positions of a run are a pure function of the run start
+// (encoder.nim:281-331), so 32 probes are hashed, looked up and compared at once; same-window
+// hash collisions are resolved to "latest earlier lane" with match.any, and only the probes up
+// to the winning one commit their table insert (last writer wins), which is exactly the table
+// state the serial loop leaves behind.
+__device__ __forceinline__ uint32_t compress_block_warp(const uint8_t* __restrict__ in, uint32_t len,
+                                                        uint8_t* __restrict__ out, uint16_t* table,
+                                                        uint32_t abort_thr, uint32_t lane) {
+  if (len < kMinNonLiteral) return emit_literal_warp(out, in, len, lane);  // :227-229
+
+  uint32_t tsize = 256;  // :27-34
+  while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
+  const uint32_t mask = tsize - 1;
+  {
+    uint32_t* t32 = (uint32_t*)table;
+    for (uint32_t i = lane; i < tsize / 2; i += 32) t32[i] = 0;
+  }
+  const uint32_t ip_limit = len - kInputMargin;  // :245
+  uint32_t ip = 0, op = 0;
+
+  for (;;) {
+    uint32_t next_emit = ip;
+    ip += 1;
+    uint32_t cand = 0;
+    bool off_end = false;
+
+    // ---------------- literal scan, 32 probes per step (:281-331)
+    uint32_t wip = ip, wskip = 32;
+    bool first = true;
+    for (;;) {
+      __syncwarp();  // table writes of the previous step / copy loop are visible
+      uint32_t p, step, sk_after;
+      if (first) {  // stride 1 for the first 32 probes whichever way the run starts
+        p = wip + lane; step = 1; sk_after = 64;
+      } else {
+        uint32_t pos = wip, sk = wskip;
+        for (uint32_t j = 0; j < lane; j++) { uint32_t st = sk >> 5; sk += st; pos += st; }
+        p = pos; step = sk >> 5; sk_after = sk + step;
+      }
+      // :318-321 -- a probe happens only if the next position stays within ip_limit
+      bool valid = (p <= ip_limit) && (p + step <= ip_limit);
+      uint32_t d = 0, h = 0x10000u + lane, tv = 0;
+      if (valid) { d = load32u(in + p); h = hash14(d, mask); tv = table[h]; }
+      uint32_t grp = __match_any_sync(kFull, h);
+      uint32_t earlier = grp & ((1u << lane) - 1u);
+      int src = earlier ? 31 - __clz((int)earlier) : (int)lane;
+      uint32_t pe = __shfl_sync(kFull, p, src);
+      uint32_t c = earlier ? pe : tv;
+      bool hit = valid && (load32u(in + c) == d);
+      uint32_t hitmask = __ballot_sync(kFull, hit);
+      uint32_t vmask = __ballot_sync(kFull, valid);
+      if (hitmask) {
+        int kh = __ffs((int)hitmask) - 1;
+        uint32_t commit = (2u << kh) - 1u;
+        uint32_t cg = grp & commit;
+        if (((commit >> lane) & 1u) && (cg >> lane) == 1u) table[h] = (uint16_t)p;
+        ip = __shfl_sync(kFull, p, kh);
+        cand = __shfl_sync(kFull, c, kh);
+        break;
+      }
+      if (vmask != kFull) { off_end = true; break; }
+      if ((grp >> lane) == 1u) table[h] = (uint16_t)p;
+      wip = __shfl_sync(kFull, p + step, 31);
+      wskip = __shfl_sync(kFull, sk_after, 31);
+      first = false;
+    }
+
+    if (off_end) {  // :319-321 -> emitRemainder from next_emit
+      uint32_t n = len - next_emit;
+      if (op + literal_size(n) > abort_thr) return kAborted;
+      return op + emit_literal_warp(out + op, in + next_emit, n, lane);
+    }
+
+    {  // :336-338
+      uint32_t n = ip - next_emit;
+      if (op + literal_size(n) > abort_thr) return kAborted;
+      op += emit_literal_warp(out + op, in + next_emit, n, lane);
+    }
+
+    // ---------------- copy loop (:350-380)
+    uint32_t matched = 4 + common_prefix_warp(in, len, cand + 4, ip + 4, lane);
+    for (;;) {
+      op += emit_copy_warp(out + op, ip - cand, matched, lane);
+      ip += matched;
+      if (op > abort_thr) return kAborted;
+      if (ip > ip_limit) {  // :362-363
+        if (ip < len) {
+          uint32_t n = len - ip;
+          if (op + literal_size(n) > abort_thr) return kAborted;
+          op += emit_literal_warp(out + op, in + ip, n, lane);
+        }
+        return op;
+      }
+      __syncwarp();
+      uint32_t d1 = load32u(in + ip - 1), d = load32u(in + ip);
+      uint32_t h1 = hash14(d1, mask), h = hash14(d, mask);
+      uint32_t tv = table[h];
+      cand = (h == h1) ? ip - 1 : tv;  // :371-377: insert ip-1, then look up / insert ip
+      __syncwarp();                    // every lane has read before lane 0 writes
+      if (lane == 0) { table[h1] = (uint16_t)(ip - 1); table[h] = (uint16_t)ip; }
+      matched = common_prefix_warp(in, len, cand, ip, lane);
+      if (matched < 4) break;          // :379-380
+    }
+  }
+}
+
+struct CompressArgs {
+  const uint8_t* in_base;
+  uint8_t* out_base;
+  const uint64_t* in_off;   // null: job i starts at i * 65536 (contiguous stream of total_len bytes)
+  const uint32_t* in_len;   // null: min(65536, total_len - i * 65536)
+  const uint64_t* out_off;  // null: i * out_stride
+  uint64_t total_len;
+  uint64_t out_stride;
+  const uint32_t* crc;      // masked CRC per job (frame mode)
+  uint32_t* out_len;        // bytes produced per job
+  uint32_t* counter;        // work queue head (zeroed before launch)
+  uint32_t count;
+  uint32_t mode;
+  uint32_t table_entries;   // per-warp shared-memory table capacity (u16 entries)
+};
+
+__device__ __forceinline__ uint32_t put_varint32(uint8_t* o, uint32_t v, uint32_t lane) {
+  uint32_t n = 0;
+  while (v >= 0x80) { if (lane == 0) o[n] = (uint8_t)(v | 0x80); v >>= 7; n++; }
+  if (lane == 0) o[n] = (uint8_t)v;
+  return n + 1;
+}
+__device__ __forceinline__ uint32_t varint32_len(uint32_t v) {
+  return v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5;
+}
+
+// One job = one encodeFrame (encoder.nim:385-426), one bare encodeBlock, or one whole
+// single-block `compress` message (snappy.nim:27-64).
+__device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job, uint16_t* table, uint32_t lane) {
+  uint64_t ioff = a.in_off ? a.in_off[job] : (uint64_t)job * kMaxBlock;
+  uint32_t len = a.in_len ? a.in_len[job] : (uint32_t)((a.total_len - ioff) < kMaxBlock ? (a.total_len - ioff) : kMaxBlock);
+  uint64_t ooff = a.out_off ? a.out_off[job] : (uint64_t)job * a.out_stride;
+  const uint8_t* in = a.in_base + ioff;
+  uint8_t* out = a.out_base + ooff;
+  uint32_t total;
+  if (a.mode == kModeFrame) {
+    uint32_t crc = a.crc[job];
+    uint32_t hl = varint32_len(len);
+    uint32_t thr = len - len / 8;
+    uint32_t bl = kAborted;
+    if (len >= kMinNonLiteral) bl = compress_block_warp(in, len, out + 8 + hl, table, thr, lane);  // :401-406
+    uint32_t fl;
+    if (bl != kAborted && bl <= thr) {  // :408-416
+      put_varint32(out + 8, len, lane);
+      fl = hl + bl + 4;
+      if (lane == 0) out[0] = 0x00;
+    } else {  // :418-426
+      fl = len + 4;
+      if (lane == 0) out[0] = 0x01;
+      warp_copy(out + 8, in, len, lane);
+    }
+    if (lane == 0) {
+      out[1] = (uint8_t)fl; out[2] = (uint8_t)(fl >> 8); out[3] = (uint8_t)(fl >> 16);
+      out[4] = (uint8_t)crc; out[5] = (uint8_t)(crc >> 8); out[6] = (uint8_t)(crc >> 16); out[7] = (uint8_t)(crc >> 24);
+    }
+    total = fl + 4;
+  } else if (a.mode == kModeRawBlock) {
+    total = len ? compress_block_warp(in, len, out, table, kNoAbort, lane) : 0;
+  } else {
+    uint32_t hl = put_varint32(out, len, lane);
+    total = hl + (len ? compress_block_warp(in, len, out + hl, table, kNoAbort, lane) : 0);
+  }
+  if (lane == 0) a.out_len[job] = total;
+}
+
+// Persistent kernel: blockDim.x/32 warps per CTA, each with its own hash table in dynamic
+// shared memory, pulling jobs from a global counter.
+__global__ void __launch_bounds__(256) compress_kernel(CompressArgs a) {
+  SNB_DYN_SMEM(smem);
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint16_t* table = (uint16_t*)smem + (size_t)warp * a.table_entries;
+  for (;;) {
+    uint32_t job = 0;
+    if (lane == 0) job = atomicAdd(a.counter, 1u);
+    job = __shfl_sync(kFull, job, 0);
+    if (job >= a.count) return;
+    compress_job(a, job, table, lane);
+    __syncwarp();
+  }
+}
+
+// ===================================================================== CRC kernels
+struct CrcArgs {
+  const uint8_t* base;
+  const uint64_t* off;   // null: i * 65536 over total_len
+  const uint32_t* len;
+  uint64_t total_len;
+  uint32_t* out;         // per job CRC
+  uint32_t count;
+  uint32_t masked;       // 1: snappy-masked, 0: plain finalised CRC-32C
+};
+__global__ void __launch_bounds__(256) crc_kernel(CrcArgs a, const CrcTables* g) {
+  __shared__ CrcSmem t;
+  crc_stage_tables(&t, g);
+  uint32_t lane = threadIdx.x & 31;
+  uint32_t wpb = blockDim.x >> 5;
+  for (uint32_t job = blockIdx.x * wpb + (threadIdx.x >> 5); job < a.count; job += gridDim.x * wpb) {
+    uint64_t o = a.off ? a.off[job] : (uint64_t)job * kMaxBlock;
+    uint32_t n = a.len ? a.len[job] : (uint32_t)((a.total_len - o) < kMaxBlock ? (a.total_len - o) : kMaxBlock);
+    uint32_t c = crc32c_warp(t, g, a.base + o, n, lane);
+    if (lane == 0) a.out[job] = a.masked ? crc_mask(c) : c;
+  }
+}
+
+// ===================================================================== scan + compaction
+// Exclusive prefix sum of lens[0..count) into offs (u64), starting at base_const + *base_ptr;
+// end offset into *total (may alias base_ptr).  One CTA.
+__global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* lens, uint64_t* offs, uint32_t count,
+                                                    const uint64_t* base_ptr, uint64_t base_const, uint64_t* total) {
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long carry_s;
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) carry_s = base_const + (base_ptr ? *base_ptr : 0ull);
+  __syncthreads();
+  for (uint32_t start = 0; start < count; start += blockDim.x) {
+    uint32_t i = start + threadIdx.x;
+    unsigned long long v = i < count ? lens[i] : 0, incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned long long u = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += u;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    unsigned long long wprefix = 0;
+    for (uint32_t w = 0; w < warp; w++) wprefix += warp_sums[w];
+    unsigned long long carry = carry_s;
+    if (i < count) offs[i] = carry + wprefix + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) {
+      unsigned long long t = 0;
+      for (uint32_t w = 0; w < nw; w++) t += warp_sums[w];
+      carry_s = carry + t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+
+// Gather variable-length job outputs (slot i at i*stride, lens[i] bytes) to dst + offs[i].
+// One CTA per job (grid-stride), dst-aligned 32-bit stores.
+__global__ void __launch_bounds__(256) compact_kernel(const uint8_t* scratch, uint64_t stride, const uint32_t* lens,
+                                                      const uint64_t* offs, uint8_t* dst, uint32_t count) {
+  for (uint32_t job = blockIdx.x; job < count; job += gridDim.x) {
+    const uint8_t* s = scratch + (uint64_t)job * stride;
+    uint8_t* d = dst + offs[job];
+    uint32_t n = lens[job];
+    uint32_t head = umin32(n, (uint32_t)((0 - (uintptr_t)d) & 3));
+    if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
+    uint32_t words = (n - head) >> 2;
+    uint32_t* dw = (uint32_t*)(d + head);
+    const uint8_t* sp = s + head;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dw[i] = load32u(sp + 4 * i);
+    uint32_t done = head + 4 * words;
+    if (threadIdx.x < n - done) d[done + threadIdx.x] = s[done + threadIdx.x];
+  }
+}
+
+// ===================================================================== decompress
+// One chunk / message descriptor.  For framed chunks the host's header walk fills it
+// (snappy.nim:199-265); for raw batches the wrapper kernels build it from offset tables.
+struct Chunk {
+  uint64_t in_off;   // payload: varint+tags (kind 0) or raw bytes (kind 1/2)
+  uint64_t out_off;
+  uint32_t in_len;
+  uint32_t out_cap;  // room the reference would hand to `uncompress` for this chunk
+  uint32_t crc;      // stored masked CRC (framed)
+  uint32_t kind;
+};
+
+// uncompress (snappy.nim:84-110) + decodeAllTags (decoder.nim:20-155) for one message.
+// Tags are parsed 32 stream bytes at a time: every lane decodes "a tag starting at my byte",
+// pointer jumping over next-tag links marks the real tag starts, a prefix sum over their
+// lengths gives output positions, then literals / back-references that do not read bytes
+// produced inside this step copy in parallel and the (few) dependent ones follow in order.
+// Accept/reject decisions equal the reference's for every input; only bytes past `written`
+// (scratch in the reference) are left untouched here.
+__device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ in, uint32_t n, uint8_t* out,
+                                                   uint32_t cap, uint32_t* written, uint32_t lane) {
+  *written = 0;
+  // ---- u32 varint (stew/leb128 via snappy.nim:92-94)
+  uint32_t ulen = 0, br = 0;
+  {
+    bool done = false, bad = false;
+    for (uint32_t i = 0; i < 5 && !done && !bad; i++) {
+      if (i >= n) { bad = true; break; }
+      uint32_t b = in[i];
+      if (i == 4 && (b & 0xf0)) { bad = true; break; }
+      ulen |= (b & 0x7f) << (7 * i);
+      if (!(b & 0x80)) { done = true; br = i + 1; }
+    }
+    if (!done) return kInvalidInput;
+  }
+  if (cap < ulen) return kBufferTooSmall;                      // :96-97
+  if (ulen == 0) return br != n ? kInvalidInput : kOk;         // :99-102
+  if (ulen > kMaxDeviceMessage || n - br > kMaxDeviceMessage) return kUnsupported;
+
+  const uint8_t* tags = in + br;
+  const uint32_t tn = n - br;
+  const uint32_t lim = ulen;  // decisions are identical for any cap >= ulen
+  uint32_t ip = 0, op = 0;
+
+  while (ip < tn) {
+    __syncwarp();  // output bytes of the previous step are visible to every lane
+    uint32_t pos = ip + lane;
+    bool inb = pos < tn;
+    uint32_t avail = inb ? tn - pos : 0;
+    uint32_t t = 0, v4 = 0;
+    if (inb) { t = tags[pos]; v4 = load_upto4(tags + pos + 1, umin32(avail - 1, 4)); }
+    uint32_t kind = t & 3, L, hdr = 1, off = 0, size;
+    bool bad = false;
+    if (kind == 0) {
+      L = (t >> 2) + 1;
+      if (L >= 61) {                                           // decoder.nim:54-75
+        uint32_t ll = L - 60;
+        if (avail - 1 < 61) bad = true;
+        uint32_t m = ll == 4 ? 0xffffffffu : ((1u << (8 * ll)) - 1u);
+        L = (v4 & m) + 1;
+        if (L == 0) bad = true;
+        hdr = 1 + ll;
+      }
+      if (!bad && avail - hdr < L) bad = true;                 // :77-79 (input side)
+      size = hdr + L;
+    } else if (kind == 1) {                                    // :87-94
+      bad = avail < 2; L = 4 + ((t >> 2) & 7); off = ((t & 0xe0) << 3) | (v4 & 0xff); size = 2;
+    } else if (kind == 2) {                                    // :95-102
+      bad = avail < 3; L = 1 + (t >> 2); off = v4 & 0xffff; size = 3;
+    } else {                                                   // :103-109
+      bad = avail < 5; L = 1 + (t >> 2); off = v4; size = 5;
+    }
+    if (bad) size = 64;
+    uint32_t J = inb ? umin32(lane + size, 32) : 32;
+    uint32_t R = 1u;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {  // 2^4 = 16 >= tags in 32 bytes (every element is >= 2 bytes)
+      uint32_t contrib = (((R >> lane) & 1u) && J < 32) ? (1u << J) : 0u;
+      R |= __reduce_or_sync(kFull, contrib);
+      uint32_t jn = __shfl_sync(kFull, J, (int)(J & 31));
+      J = J < 32 ? jn : 32;
+    }
+    bool is_tag = inb && ((R >> lane) & 1u);
+    uint32_t val = (is_tag && !bad) ? L : 0, incl = val;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t u = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += u;
+    }
+    uint32_t my_op = op + (incl - val);
+    bool e = is_tag && bad;
+    if (is_tag && !bad) {
+      if (kind != 0 && (off == 0 || off > my_op)) e = true;    // :112-113
+      if (my_op > lim || lim - my_op < L) e = true;            // :77, :127
+    }
+    if (__any_sync(kFull, e)) return kInvalidInput;
+
+    bool go = is_tag;
+    bool dep = go && kind != 0 && (my_op - off + umin32(L, off) > op);
+    bool shrt = go && !dep && L <= 16;
+    if (shrt) {
+      uint8_t* d = out + my_op;
+      if (kind == 0) {
+        const uint8_t* s = tags + pos + hdr;
+        for (uint32_t i = 0; i < L; i++) d[i] = s[i];
+      } else {
+        const uint8_t* s = out + my_op - off;  // off >= 1; byte-serial forward copy handles overlap
+        for (uint32_t i = 0; i < L; i++) d[i] = s[i];
+      }
+    }
+    uint32_t lmask = __ballot_sync(kFull, go && !dep && L > 16);
+    uint32_t dmask = __ballot_sync(kFull, dep);
+    while (lmask) {
+      int s = __ffs((int)lmask) - 1;
+      lmask &= lmask - 1;
+      uint32_t so = __shfl_sync(kFull, my_op, s), sl = __shfl_sync(kFull, L, s);
+      uint32_t sk = __shfl_sync(kFull, kind, s);
+      uint32_t sx = __shfl_sync(kFull, kind == 0 ? pos + hdr : off, s);
+      const uint8_t* srcp = sk == 0 ? tags + sx : out + so - sx;
+      if (sk == 0 || sx >= sl) {
+        warp_copy(out + so, srcp, sl, lane);
+      } else {
+        for (uint32_t i = lane; i < sl; i += 32) out[so + i] = srcp[i % sx];
+      }
+    }
+    while (dmask) {
+      __syncwarp();
+      int s = __ffs((int)dmask) - 1;
+      dmask &= dmask - 1;
+      uint32_t so = __shfl_sync(kFull, my_op, s), sl = __shfl_sync(kFull, L, s), sx = __shfl_sync(kFull, off, s);
+      const uint8_t* srcp = out + so - sx;
+      if (sx >= sl) { for (uint32_t i = lane; i < sl; i += 32) out[so + i] = srcp[i]; }
+      else { for (uint32_t i = lane; i < sl; i += 32) out[so + i] = srcp[i % sx]; }
+    }
+    uint32_t tagmask = __ballot_sync(kFull, is_tag);
+    int last = 31 - __clz((int)tagmask);
+    ip = __shfl_sync(kFull, pos + size, last);
+    op += __shfl_sync(kFull, incl, 31);
+  }
+  if (op != ulen) return kInvalidInput;                        // snappy.nim:107-108
+  *written = op;
+  return kOk;
+}
+
+struct DecompressArgs {
+  const uint8_t* in_base;
+  uint8_t* out_base;
+  const Chunk* chunks;
+  int32_t* status;     // per chunk
+  uint32_t* out_len;   // per chunk bytes produced
+  uint32_t* counter;
+  uint32_t count;
+  uint32_t verify;     // 1: compare masked CRC of the produced bytes with chunk.crc
+};
+
+__global__ void __launch_bounds__(256) decompress_kernel(DecompressArgs a, const CrcTables* g) {
+  __shared__ CrcSmem t;
+  if (a.verify) crc_stage_tables(&t, g);
+  uint32_t lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t job = 0;
+    if (lane == 0) job = atomicAdd(a.counter, 1u);
+    job = __shfl_sync(kFull, job, 0);
+    if (job >= a.count) return;
+    Chunk c = a.chunks[job];
+    const uint8_t* in = a.in_base + c.in_off;
+    uint8_t* out = a.out_base + c.out_off;
+    int32_t st = kOk;
+    uint32_t w = 0;
+    const uint8_t* produced = out;
+    if (c.kind == kKindCompressed) {
+      st = decompress_warp(in, c.in_len, out, c.out_cap, &w, lane);
+    } else if (c.kind == kKindStored) {
+      warp_copy(out, in, c.in_len, lane);
+      w = c.in_len;
+    } else {
+      produced = in; w = c.in_len;
+    }
+    if (st == kOk && a.verify) {
+      __syncwarp();
+      uint32_t crc = crc_mask(crc32c_warp(t, g, produced, w, lane));
+      if (crc != c.crc) st = kCrcMismatch;
+    }
+    if (lane == 0) { a.status[job] = st; a.out_len[job] = st == kOk ? w : 0; }
+    __syncwarp();
+  }
+}
+
+// Build Chunk descriptors for a raw batch from offset/length tables (device-side helper).
+__global__ void make_chunks_kernel(const uint64_t* in_off, const uint32_t* in_len, const uint64_t* out_off,
+                                   const uint32_t* out_cap, Chunk* chunks, uint32_t count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Chunk c;
+  c.in_off = in_off[i]; c.out_off = out_off[i]; c.in_len = in_len[i]; c.out_cap = out_cap[i];
+  c.crc = 0; c.kind = kKindCompressed;
+  chunks[i] = c;
+}
+
+// Uncompressed lengths of a raw batch (codec.nim:129-138 semantics, u32 range): 0xffffffff on a bad varint.
+__global__ void varint_lens_kernel(const uint8_t* base, const uint64_t* in_off, const uint32_t* in_len, uint32_t* lens,
+                                   uint32_t count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint8_t* p = base + in_off[i];
+  uint32_t n = in_len[i], v = 0;
+  bool done = false;
+  for (uint32_t k = 0; k < 5 && k < n; k++) {
+    uint32_t b = p[k];
+    if (k == 4 && (b & 0xf0)) break;
+    v |= (b & 0x7f) << (7 * k);
+    if (!(b & 0x80)) { done = true; break; }
+  }
+  lens[i] = done ? v : 0xffffffffu;
+}
+
+}  // namespace snb

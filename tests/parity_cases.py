@@ -1,0 +1,171 @@
+"""Parity checks shared by the emulator suite (CPU, small inputs) and the GPU suite (full sizes).
+
+`api` is a nim_snappy_b200.Snappy bound to either library; `o` is the oracle module.  Every check
+compares the product's bytes / statuses with the oracle's on the same input -- bit-exact, no
+tolerance: the whole path is integer / byte work."""
+import numpy as np
+
+import vectors as V
+from conftest import read_data, read_golden
+
+HDR = b"\xff\x06\x00\x00sNaPpY"
+
+
+def check_crc(api, o, sizes, seed=3):
+    rng = np.random.default_rng(seed)
+    for n in sizes:
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert api.maskedCrc(d) == o.masked_crc32c(d), n
+
+
+def check_raw(api, o, data, cpp=None):
+    """snappy.encode == oracle encode (byte-identical); decode of the oracle stream == source."""
+    enc_o = o.encode(data)
+    enc = api.encode(data)
+    assert enc == enc_o, (len(data), len(enc), len(enc_o))
+    assert api.decode(enc_o) == data
+    assert api.uncompressedLen(enc_o) == len(data)
+    if cpp is not None and len(data):
+        assert api.decode(cpp.encode(data)) == data           # tests/test_snappy.nim:68
+
+
+def check_framed(api, o, data):
+    enc_o = o.encode_framed(data)
+    enc = api.encodeFramed(data)
+    assert enc == enc_o, (len(data), len(enc), len(enc_o))
+    assert api.uncompressedLenFramed(enc_o) == len(data)
+    out = np.zeros(max(len(data), 1), dtype=np.uint8)[: len(data)]
+    assert api.uncompressFramed(enc_o, out) == (len(enc_o), len(data))
+    assert out.tobytes() == data
+    assert api.decodeFramed(enc_o) == data
+
+
+def status_of(r):
+    return 0 if not hasattr(r, "name") else int(r)
+
+
+def check_raw_decode_parity(api, o, stream, cap=None):
+    """Same status and (on success) same bytes as the oracle for an arbitrary raw stream."""
+    n = o.uncompressed_len(stream)
+    cap = (n if n is not None and n < (1 << 24) else 64) if cap is None else cap
+    st_o, out_o = o.uncompress(stream, cap)
+    buf = np.zeros(max(cap, 1), dtype=np.uint8)[:cap]
+    r = api.uncompress(stream, buf)
+    assert status_of(r) == st_o, (stream[:16], cap, r, st_o)
+    if st_o == 0:
+        assert r == len(out_o) and buf[:r].tobytes() == out_o
+
+
+def check_framed_decode_parity(api, o, stream, cap, check_header=True, check_integrity=True):
+    st_o, rd_o, wr_o, out_o = o.uncompress_framed(stream, cap, check_header, check_integrity)
+    buf = np.zeros(max(cap, 1), dtype=np.uint8)[:cap]
+    r = api.uncompressFramed(stream, buf, check_header, check_integrity)
+    assert status_of(r) == st_o, (stream[:24], cap, r, st_o)
+    if st_o == 0:
+        assert r == (rd_o, wr_o)
+        assert buf[:wr_o].tobytes() == out_o
+    return r
+
+
+def check_malformed(api, o):
+    for enc in V.MALFORMED_RAW:                               # tests/test_snappy.nim:161-218
+        assert api.decode(enc) == b""
+        check_raw_decode_parity(api, o, enc)
+        check_raw_decode_parity(api, o, enc, cap=64)
+    for enc, dec in V.HANDBUILT_RAW:                          # :136-148
+        assert api.decode(enc) == dec
+    assert api.encode(b"") == b"\x00"                         # :163-165
+    assert api.decode(b"\x00") == b""
+    assert api.decode(b"") == b""
+
+
+def check_framed_fixture(api, o, fixture, source):
+    """tests/test_framed.nim:9-59 incl. the partial-output / resume contract."""
+    comp, expected = read_golden(fixture), read_data(source)
+    assert api.decodeFramed(comp) == expected
+    assert api.uncompressedLenFramed(comp) == len(expected)
+    check_framed_decode_parity(api, o, comp, len(expected))
+    r = check_framed_decode_parity(api, o, comp, len(expected) - 1)
+    rd, wr = r
+    assert rd < len(comp) and wr < len(expected)
+    buf = np.zeros(len(expected) - wr, dtype=np.uint8)
+    r2 = api.uncompressFramed(comp[rd:], buf, False)
+    assert r2 == (len(comp) - rd, len(expected) - wr)
+    assert buf.tobytes() == expected[wr:]
+
+
+def check_framed_edges(api, o, full=True):
+    """tests/test_framed.nim:137-219."""
+    out0 = np.zeros(1, dtype=np.uint8)[:0]
+    assert api.uncompressFramed(HDR, out0) == (10, 0)         # just a header
+    assert api.decodeFramed(HDR) == b""
+    buf = bytes(i & 0xFF for i in range(128 * 1024))
+    sizes = [0, 1, 10, 16, 17, 18, 65535, 65536, 65537, 131072] if full else [0, 1, 10, 16, 17, 18, 65537]
+    for n in sizes:                                           # buffer sizes
+        check_framed(api, o, buf[:n])
+    data = bytes(65536)
+    crc = o.masked_crc32c(data).to_bytes(4, "little")
+    comp = o.encode(data)
+    framed = HDR + b"\x01" + (len(data) + 4).to_bytes(3, "little") + crc + data
+    framed_c = HDR + b"\x00" + (len(comp) + 4).to_bytes(3, "little") + crc + comp
+    for f in (framed, framed_c):                              # full uncompressed / compressed chunk
+        assert api.decodeFramed(f) == data
+        check_framed_decode_parity(api, o, f, 65536)
+    zero = bytes(4)
+    f0 = HDR + b"\x01" + (len(data) + 4).to_bytes(3, "little") + zero + data
+    f0c = HDR + b"\x00" + (len(comp) + 4).to_bytes(3, "little") + zero + comp
+    for f in (f0, f0c):                                       # checkIntegrity
+        check_framed_decode_parity(api, o, f, 65536)                        # crcMismatch
+        check_framed_decode_parity(api, o, f, 65536, check_integrity=False)  # accepted
+        assert api.decodeFramed(f, checkIntegrity=False) == data
+        assert api.decodeFramed(f) == b""
+    for payload, n in V.INVALID_FRAMED:                       # invalid header
+        check_framed_decode_parity(api, o, payload, n)
+        assert api.decodeFramed(payload) == b""
+        assert api.uncompressedLenFramed(payload) is None
+    big = bytes(65537)                                        # overlong frame, both chunk types
+    bcrc = o.masked_crc32c(big).to_bytes(4, "little")
+    bcomp = o.encode(big)
+    for f in (HDR + b"\x01" + (len(big) + 4).to_bytes(3, "little") + bcrc + big,
+              HDR + b"\x00" + (len(bcomp) + 4).to_bytes(3, "little") + bcrc + bcomp):
+        check_framed_decode_parity(api, o, f, len(big))
+        assert api.decodeFramed(f) == b""
+        assert api.uncompressedLenFramed(f) is None
+    # overlong stored chunk with a wrong CRC: crcMismatch outranks invalidInput (snappy.nim:244-251)
+    check_framed_decode_parity(api, o, HDR + b"\x01" + (len(big) + 4).to_bytes(3, "little") + zero + big, len(big))
+    # unknown / skippable / padding chunks and a repeated stream identifier (snappy.nim:259-263)
+    small = o.encode_framed(b"hello hello hello hello hello")[10:]
+    check_framed_decode_parity(api, o, HDR + b"\x02\x01\x00\x00x" + small, 64)
+    check_framed_decode_parity(api, o, HDR + b"\x80\x01\x00\x00x" + small + b"\xfe\x02\x00\x00pp" + HDR + small, 64)
+    check_framed_decode_parity(api, o, HDR + small + b"\x00\x00", 64)       # trailing < 4 bytes
+    check_framed_decode_parity(api, o, HDR + b"\x00\x03\x00\x00abc", 64)    # dataLen < 4
+    check_framed_decode_parity(api, o, HDR + small[:-1], 64)                # truncated chunk
+    check_framed_decode_parity(api, o, small, 64)                           # no header, checkHeader = true
+    check_framed_decode_parity(api, o, small, 64, check_header=False)
+    check_framed_decode_parity(api, o, HDR + small, 5)                      # output too small: partial (10, 0)
+    stored = HDR + b"\x01\x09\x00\x00" + o.masked_crc32c(b"abcde").to_bytes(4, "little") + b"abcde"
+    check_framed_decode_parity(api, o, stored + small, 3)                   # stored chunk does not fit
+    check_framed_decode_parity(api, o, stored[:-5] + b"abcdX" + small, 3)   # ... and its CRC is wrong
+    check_framed_decode_parity(api, o, stored + small, 5)                   # fits, next one does not
+
+
+def mutate_streams(o, base, rng, count):
+    """Differential-fuzz inputs in the spirit of tests/fuzzing/fuzz_block_format.nim: valid streams
+    with byte flips, truncations and insertions."""
+    out = []
+    for _ in range(count):
+        b = bytearray(base)
+        kind = rng.integers(0, 4)
+        if kind == 0 and len(b) > 1:
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1 and len(b) > 1:
+            b = b[: int(rng.integers(1, len(b)))]
+        elif kind == 2:
+            i = int(rng.integers(0, len(b) + 1))
+            b[i:i] = bytes(rng.integers(0, 256, int(rng.integers(1, 6)), dtype=np.uint8))
+        else:
+            i = int(rng.integers(0, len(b)))
+            b[i] = int(rng.integers(0, 256))
+        out.append(bytes(b))
+    return out

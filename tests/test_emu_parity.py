@@ -1,0 +1,82 @@
+"""CPU-only parity of the PRODUCT sources (csrc/snb_device.cuh + snb_api.cu) compiled against the
+SIMT emulator in tests/emu: the kernels' warp-level logic and the host chunk drivers are checked
+against the oracle without a GPU.  Sizes are small because every warp collective costs 32 fiber
+switches; the full-size parity runs on the B200 in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import parity_cases as P
+import vectors as V
+from conftest import read_data
+
+
+def test_crc(emu_api, oracle):
+    P.check_crc(emu_api, oracle, [0, 1, 3, 4, 5, 15, 16, 17, 511, 512, 513, 527, 528, 1500, 4096, 21017, 65536, 70000])
+    alice = read_data("alice29.txt")
+    assert [emu_api.maskedCrc(alice[i:i + 65536]) for i in range(0, len(alice), 65536)] == V.ALICE_CHUNK_CRCS
+
+
+def test_crc_unaligned(emu_api, oracle):
+    base = np.frombuffer(read_data("html")[:70000], dtype=np.uint8)
+    for mis in (1, 3, 8, 13):
+        d = base[mis:mis + 66000]
+        assert emu_api.maskedCrc(d) == oracle.masked_crc32c(d)
+
+
+@pytest.mark.parametrize("name,limit", [("alice29.txt", 70000), ("html", 66000), ("geo.protodata", 40000),
+                                        ("fireworks.jpeg", 66000), ("kppkn.gtb", 30000), ("urls.10K", 50000),
+                                        ("Mark.Twain-Tom.Sawyer.txt", None)])
+def test_corpus_prefixes(emu_api, oracle, name, limit):
+    d = read_data(name)[:limit]
+    P.check_raw(emu_api, oracle, d, oracle.ref_snappycpp())
+    P.check_framed(emu_api, oracle, d)
+
+
+def test_small_and_boundary_sizes(emu_api, oracle):
+    for i in range(1, 33, 3):                                  # tests/test_snappy.nim:111-114
+        P.check_raw(emu_api, oracle, b"aaaa" + b"b" * i + b"aaaabbbb")
+    pat = bytes((j % 10) + ord("a") for j in range(70000))
+    for n in [1, 2, 15, 16, 17, 18, 31, 32, 33, 47, 64, 100, 255, 256, 257, 1000, 4095, 4096, 4097, 16385]:
+        P.check_raw(emu_api, oracle, pat[:n])
+        P.check_raw(emu_api, oracle, bytes(n))
+    for n in (65531, 65536, 65541):                            # :124-134 (m = 1)
+        P.check_raw(emu_api, oracle, pat[:n])
+        P.check_raw(emu_api, oracle, bytes(n))
+    for w in V.WITNESSES:                                      # :222-245
+        P.check_raw(emu_api, oracle, w)
+    assert len(emu_api.encode(bytes(1024))) < 512              # :150-154
+
+
+def test_random_strings(emu_api, oracle):
+    rng = np.random.default_rng(11)
+    for _ in range(12):                                        # tests/test_snappy.nim:247-253 (seeded here)
+        n = int(rng.integers(1000, 10000))
+        alphabet = int(rng.integers(2, 64))
+        P.check_raw(emu_api, oracle, rng.integers(0, alphabet, n, dtype=np.uint8).tobytes())
+    P.check_raw(emu_api, oracle, rng.integers(0, 256, 20000, dtype=np.uint8).tobytes())
+
+
+def test_malformed(emu_api, oracle):
+    P.check_malformed(emu_api, oracle)
+
+
+def test_framed_fixture_house(emu_api, oracle):
+    P.check_framed_fixture(emu_api, oracle, "house.jpg.sz", "house.jpg")
+
+
+def test_framed_fixture_alice(emu_api, oracle):
+    P.check_framed_fixture(emu_api, oracle, "alice29.txt.sz-64k", "alice29.txt")
+
+
+def test_framed_edges(emu_api, oracle):
+    P.check_framed_edges(emu_api, oracle, full=False)
+
+
+def test_decoder_differential_fuzz(emu_api, oracle):
+    rng = np.random.default_rng(5)
+    base = oracle.encode(read_data("alice29.txt")[:3000])
+    for s in P.mutate_streams(oracle, base, rng, 60):
+        P.check_raw_decode_parity(emu_api, oracle, s)
+    fbase = oracle.encode_framed(read_data("html")[:2000] + bytes(rng.integers(0, 256, 300, dtype=np.uint8)))
+    for s in P.mutate_streams(oracle, fbase, rng, 40):
+        P.check_framed_decode_parity(emu_api, oracle, s, 4096)
