@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- framed compress / uncompress throughput of the B200-native Snappy codec.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3            (our CUDA path)
+    python bench.py --impl reference --steps 3 --warmup 1    (the reference algorithm on host cores)
+    torchrun ... bench.py --gpus N ...                       (one rank per GPU, weak scaling)
+
+One "step" = one framed compress of the per-GPU workload (BASELINE.json configs[1]: 1 GiB text-like
+corpus = 16384 independent 64 KiB chunks), input already resident in HBM; `value` = GB/s of
+uncompressed data over all ranks.  The same run also times framed uncompress of the resulting
+stream (configs[2]) and reports it under "uncompress".  `e2e` is the same metric through the
+host-buffer C-ABI calls (snb_compress_framed / snb_uncompress_framed) with pinned host buffers,
+H2D and D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "framed compress GB/s of uncompressed input (uncompress reported alongside)"
+UNIT = "GB/s"
+CHUNK = 65536
+
+
+def rank_info():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU reference (oracle, all host threads)
+class CpuReference:
+    """The reference algorithm (oracle/ restatement of encodeFrame / uncompressFramed) run over
+    statically partitioned chunk ranges on `threads` host threads (ctypes releases the GIL)."""
+
+    def __init__(self, threads=None):
+        from oracle import oracle as o
+        o.build()
+        self.o, self.lib = o, o.lib()
+        self.threads = threads or (os.cpu_count() or 1)
+
+    def _run(self, fn, parts):
+        res = [None] * len(parts)
+
+        def work(i):
+            res[i] = fn(*parts[i])
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(len(parts))]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0, res
+
+    def compress_framed(self, data, outs=None):
+        """-> (seconds, list of per-thread output arrays, list of byte counts)."""
+        n = data.size
+        nchunks = (n + CHUNK - 1) // CHUNK
+        T = min(self.threads, max(nchunks, 1))
+        per = (nchunks + T - 1) // T
+        ranges = [(i * per, min(per, nchunks - i * per)) for i in range(T) if i * per < nchunks]
+        if outs is None:
+            outs = [np.empty(c * (CHUNK + 8) + 76490, dtype=np.uint8) for _, c in ranges]
+        parts = [(data.ctypes.data, n, f, c, outs[i].ctypes.data) for i, (f, c) in enumerate(ranges)]
+        dt, written = self._run(self.lib.orc_encode_frames_range, parts)
+        return dt, outs, written
+
+    def framed_stream(self, data):
+        dt, outs, written = self.compress_framed(data)
+        return dt, np.concatenate([np.frombuffer(b"\xff\x06\x00\x00sNaPpY", dtype=np.uint8)] +
+                                  [o[:w] for o, w in zip(outs, written)])
+
+    def uncompress_framed(self, stream, total_out, out=None):
+        """Walks the chunk headers (cheap), then decodes chunk ranges on all threads."""
+        import ctypes as C
+        offs, pos, n = [], 10, stream.size
+        hdr = stream
+        while pos < n:
+            offs.append(pos)
+            pos += 4 + (int(hdr[pos + 1]) | (int(hdr[pos + 2]) << 8) | (int(hdr[pos + 3]) << 16))
+        nchunks = len(offs)
+        T = min(self.threads, max(nchunks, 1))
+        per = (nchunks + T - 1) // T
+        if out is None:
+            out = np.empty(total_out, dtype=np.uint8)
+        parts, keep = [], []
+        for i in range(T):
+            if i * per >= nchunks:
+                break
+            rd, wr = C.c_size_t(0), C.c_size_t(0)
+            keep.append((rd, wr))
+            o0 = i * per * CHUNK
+            parts.append((stream.ctypes.data, n, offs[i * per], per, out.ctypes.data + o0, total_out - o0,
+                          C.byref(rd), C.byref(wr)))
+        dt, st = self._run(self.lib.orc_uncompress_frames_range, parts)
+        assert not any(st), st
+        return dt, out
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def workload_name(nbytes):
+    return (f"framed compress of a {nbytes / (1 << 30):g} GiB text-like corpus per GPU (tests/data "
+            "alice29|asyoulik|lcet10|plrabn12|html|urls.10K tiled, BASELINE configs[1]; uncompress = configs[2])")
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank, _, world = rank_info()
+    if rank != 0:
+        return
+    from nim_snappy_b200.workloads import text_corpus
+    ref = CpuReference()
+    data = text_corpus(args.bytes)
+    outs = None
+    times_c = []
+    stream = None
+    for i in range(args.warmup + args.steps):
+        dt, outs, written = ref.compress_framed(data, outs)
+        if i >= args.warmup:
+            times_c.append(dt)
+    _, stream = ref.framed_stream(data)
+    out = np.empty(data.size, dtype=np.uint8)
+    times_d = []
+    for i in range(args.warmup + args.steps):
+        dt, out = ref.uncompress_framed(stream, data.size, out)
+        if i >= args.warmup:
+            times_d.append(dt)
+    assert np.array_equal(out, data)
+    ms = 1e3 * sum(times_c) / len(times_c)
+    val = data.size / (ms * 1e-3) / 1e9
+    dval = data.size / (sum(times_d) / len(times_d)) / 1e9
+    sample = f"whole {data.size / (1 << 30):g} GiB corpus per step, chunk ranges statically split over {ref.threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(args.bytes), "bytes_per_gpu": args.bytes, "chunks_per_gpu": args.bytes // CHUNK,
+                   "note": "reference algorithm (oracle/ C restatement of nim-snappy: Nim toolchain absent) on host cores"},
+        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": ref.threads, "kind": "port", "sample": sample,
+                         "cpu": cpu_model()},
+        "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "uncompress": {"value": round(dval, 4), "unit": UNIT},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = rank_info()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import nim_snappy_b200 as snappy
+    from nim_snappy_b200 import _lib
+    from nim_snappy_b200.codec import maxCompressedLenFramed
+    from nim_snappy_b200.device import DeviceCodec
+    from nim_snappy_b200.workloads import text_corpus
+
+    lib = _lib.default()
+    dc = DeviceCodec(lib)
+    n = args.bytes
+    # every rank compresses its own shard of the (conceptually N x 1 GiB) corpus: contiguous chunk
+    # ranges, no data-path collective; shard r starts r*7919 bytes into the tile so shards differ
+    host_in = torch.from_numpy(text_corpus(n, phase=rank * 7919)).pin_memory()
+    d_in = host_in.cuda()
+    cap = maxCompressedLenFramed(n)
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_back = torch.empty(n, dtype=torch.uint8, device="cuda")
+    gather = torch.zeros(world, dtype=torch.int64, device="cuda") if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def compress_step():
+        _, w = dc.compress_framed(d_in, out=d_out, with_header=(rank == 0))
+        if world > 1:  # the only cross-GPU traffic: the per-shard length table
+            dist.all_gather_into_tensor(gather, torch.tensor([w], dtype=torch.int64, device="cuda"))
+        return w
+
+    # ---- compress: warm-up, then K timed steps on the current stream
+    for _ in range(args.warmup):
+        written = compress_step()
+    dc.set_profiling(True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    launches0 = lib.snb_kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = {"crc_ms": 0.0, "compress_ms": 0.0, "scan_ms": 0.0, "compact_ms": 0.0}
+    ev0.record()
+    for _ in range(args.steps):
+        written = compress_step()
+        p = dc.profile()
+        for k in kern_ms:
+            kern_ms[k] += p[k]
+    ev1.record()
+    barrier()
+    launches_c = lib.snb_kernel_launches() - launches0
+    c_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    dc.set_profiling(False)
+
+    # ---- uncompress of the stream just produced (byte-identical to the oracle's, see tests)
+    stream_host = d_out[:written].cpu().numpy()
+    chunks, walk = dc.frame_index(stream_host, check_header=(rank == 0))
+    assert walk.status == 0 and walk.written == n, (walk.status, walk.written)
+    d_stream = d_out[:written]
+    for _ in range(args.warmup):
+        status = dc.uncompress_chunks(d_stream, chunks, d_back)
+    dc.set_profiling(True)
+    barrier()
+    launches1 = lib.snb_kernel_launches()
+    dec_kernel_ms = 0.0
+    ev0.record()
+    for _ in range(args.steps):
+        status = dc.uncompress_chunks(d_stream, chunks, d_back)
+        dec_kernel_ms += dc.profile()["decompress_ms"]
+    ev1.record()
+    barrier()
+    launches_d = lib.snb_kernel_launches() - launches1
+    d_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    dc.set_profiling(False)
+    clock_info = clocks.stop()
+    assert not status.any(), "decode reported errors"
+    roundtrip_ok = bool((d_back == d_in).all())
+    assert roundtrip_ok, "GPU round trip differs from the input"
+
+    # ---- end to end through the host-buffer C ABI (pinned buffers; H2D + kernels + D2H per step)
+    api = snappy.Snappy(lib)
+    host_out = torch.empty(cap + (0 if rank == 0 else 10), dtype=torch.uint8).pin_memory()
+    host_back = torch.empty(n, dtype=torch.uint8).pin_memory()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(min(args.warmup, 2)):
+        w_e2e = api.compressFramed(host_in.numpy(), host_out.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        w_e2e = api.compressFramed(host_in.numpy(), host_out.numpy())
+    torch.cuda.synchronize()
+    e2e_c = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    stream_e2e = host_out.numpy()[:w_e2e]
+    for _ in range(min(args.warmup, 2)):
+        r = api.uncompressFramed(stream_e2e, host_back.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = api.uncompressFramed(stream_e2e, host_back.numpy())
+    torch.cuda.synchronize()
+    e2e_d = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    assert r == (w_e2e, n) and np.array_equal(host_back.numpy(), host_in.numpy())
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on all host cores + bit-exact check
+    cpu = None
+    verified = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        ref = CpuReference()
+        best, stream = None, None
+        for _ in range(2):
+            dt, s = ref.framed_stream(host_in.numpy())
+            best = dt if best is None else min(best, dt)
+            stream = s
+        verified = bool(stream.size == written and np.array_equal(stream, stream_host))
+        ref1 = CpuReference(threads=1)
+        dt1, _, _ = ref1.compress_framed(host_in.numpy()[: 128 << 20])
+        dtd, _ = ref.uncompress_framed(stream, n)
+        cpu = {"value": round(n / best / 1e9, 4), "unit": UNIT, "cores": ref.threads, "kind": "port",
+               "sample": f"whole {n / (1 << 30):g} GiB corpus, best of 2, chunk ranges over {ref.threads} threads",
+               "cpu": cpu_model(), "single_thread_value": round((128 << 20) / dt1 / 1e9, 4),
+               "uncompress_value": round(n / dtd / 1e9, 4)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
+    total_in = n * world
+    ck_ms = kern_ms["compress_ms"] / args.steps
+    dk_ms = dec_kernel_ms / args.steps
+    alg_bytes = n + written
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except (OSError, ValueError):
+        pass
+    line = {
+        "metric": METRIC, "value": round(total_in / (c_ms * 1e-3) / 1e9, 3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(c_ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(n), "bytes_per_gpu": n, "chunks_per_gpu": n // CHUNK,
+                   "compressed_bytes_rank0": int(written), "parallelism": f"{world} independent shard(s), one rank per GPU",
+                   "l2_policy": "inputs (1 GiB/GPU) larger than L2 (126 MB); no flush between steps",
+                   "verified_vs_oracle": verified, "roundtrip_ok": roundtrip_ok},
+        "clocks": clock_info,
+        "roofline": {"bound": "hbm", "kernel": "snb::compress_kernel", "achieved": round(alg_bytes / (ck_ms * 1e-3) / 1e9, 3),
+                     "peak": peak, "unit": "GB/s", "frac": round(alg_bytes / (ck_ms * 1e-3) / 1e9 / peak, 5),
+                     "traffic": (traffic or {}).get("compress_kernel_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": round(ck_ms, 4), "peak_source": peak_src,
+                     "step_kernels_ms": {k: round(v / args.steps, 4) for k, v in kern_ms.items()}},
+        "e2e": {"value": round(total_in / e2e_c / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": int(n),
+                "d2h_bytes_per_step": int(w_e2e), "steps": e2e_steps, "api": "snb_compress_framed (pinned host buffers)"},
+        "uncompress": {
+            "value": round(total_in / (d_ms * 1e-3) / 1e9, 3), "unit": UNIT, "ms_per_step": round(d_ms, 4),
+            "roofline": {"bound": "hbm", "kernel": "snb::decompress_kernel", "achieved": round(alg_bytes / (dk_ms * 1e-3) / 1e9, 3),
+                         "peak": peak, "unit": "GB/s", "frac": round(alg_bytes / (dk_ms * 1e-3) / 1e9 / peak, 5),
+                         "traffic": (traffic or {}).get("decompress_kernel_bytes_per_launch"), "kernel_ms": round(dk_ms, 4)},
+            "e2e": {"value": round(total_in / e2e_d / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": int(w_e2e),
+                    "d2h_bytes_per_step": int(n), "api": "snb_uncompress_framed (pinned host buffers)"},
+            "gpu_launches": int(launches_d)},
+        "gpu_launches": int(launches_c),
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bytes", type=int, default=1 << 30, help="uncompressed bytes per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.bytes = max(CHUNK, args.bytes // CHUNK * CHUNK)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        import __graft_entry__ as g
+        rank, _, _ = rank_info()
+        if rank == 0:
+            g.build()
+        else:  # the prebuilt .so normally travels with the snapshot; otherwise wait for rank 0's build
+            for _ in range(600):
+                if os.path.exists(g.LIB):
+                    break
+                time.sleep(0.5)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
