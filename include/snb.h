@@ -138,6 +138,8 @@ int snb_get_profile(float *ms, int n);
 uint64_t snb_kernel_launches(void);
 /* Tuning: warps per CTA of the compress kernel for 64 KiB blocks (hash tables are 32 KiB each). */
 void snb_set_compress_warps(int warps);
+/* Tuning / A-B testing: 1 = per-step warp encoder (v1), 2 = window-resolve encoder (default). */
+void snb_set_compress_algo(int algo);
 
 #ifdef __cplusplus
 }

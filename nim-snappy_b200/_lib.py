@@ -57,6 +57,7 @@ SIGNATURES = {
     "snb_get_profile": (_i, [C.POINTER(C.c_float), _i]),
     "snb_kernel_launches": (_u64, []),
     "snb_set_compress_warps": (None, [_i]),
+    "snb_set_compress_algo": (None, [_i]),
 }
 
 

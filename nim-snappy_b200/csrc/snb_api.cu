@@ -85,6 +85,7 @@ struct Ctx {
   uint64_t launches = 0;
   uint32_t call_launches = 0;
   int compress_warps = 6;
+  int compress_algo = 2;
   std::string err;
 };
 Ctx g;
@@ -294,6 +295,7 @@ int dev_compress_contig(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
     CKS(next_counter(st, &a.counter));
     CompressGeom cg = compress_geom((uint32_t)kChunk, cnt);
     a.table_entries = cg.entries;
+    a.algo = (uint32_t)g.compress_algo;
     if (p) prof_mark(2, st);
     SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
     count_launch();
@@ -801,6 +803,7 @@ int snb_dev_compress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const 
   CKS(next_counter(st, &a.counter));
   CompressGeom cg = compress_geom(max_len, (uint32_t)count);
   a.table_entries = cg.entries;
+  a.algo = (uint32_t)g.compress_algo;
   prof_mark(2, st);
   SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
   count_launch();
@@ -866,5 +869,6 @@ int snb_get_profile(float* ms, int n) {
 }
 uint64_t snb_kernel_launches(void) { return g.launches; }
 void snb_set_compress_warps(int warps) { g.compress_warps = warps; }
+void snb_set_compress_algo(int algo) { g.compress_algo = algo; }
 
 }  // extern "C"

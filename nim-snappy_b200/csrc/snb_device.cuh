@@ -334,6 +334,276 @@ __device__ __forceinline__ uint32_t compress_block_warp(const uint8_t* __restric
   }
 }
 
+// --------------------------------------------------------------------- encodeBlock, v2
+// Same byte-exact parse as compress_block_warp, organised around 32-position windows so that
+// the expensive work is done once per window instead of once per parse step:
+//
+//   phase A (wide): lane l owns position b+l: 8 input bytes, hash, table entry T as of the
+//            window start, 8 candidate bytes, match length ml (0..8) against T, and the
+//            match.any group of its hash.
+//   phase B (uniform): the greedy parse walks the window using those per-lane results through
+//            shuffles.  `ins` is the set of window positions inserted so far (probe positions,
+//            and ip-1 / ip after a copy -- insertion time is monotone in position).  A lane's
+//            precomputed result is exact unless an earlier lane of its hash group has been
+//            inserted in this window (grp & ins != 0); then the candidate is that lane and the
+//            match is re-measured (rare: a 4-byte repeat inside 32 bytes).
+//   commit: for every inserted lane that is the last inserted one of its group, table[h] = p
+//            -- the table the serial loop would have left.
+//
+// Literal runs use stride-1 probes only for their first 32 probes (encoder.nim:281-331: 16
+// unrolled + skip 48..63, or skip 32..63 near the end); longer runs (incompressible data) fall
+// back to the strided 32-probe windows of v1.
+struct InView {
+  const uint32_t* w;  // 4-byte aligned base (global memory)
+  uint32_t mis;       // byte offset of position 0 inside w[0]
+  uint32_t last;      // index of the last word holding input bytes
+};
+__device__ __forceinline__ uint32_t in_ld4(const InView& v, uint32_t p) {
+  uint32_t i = p + v.mis, k = i >> 2;
+  uint32_t lo = __ldg(v.w + k), hi = __ldg(v.w + umin32(k + 1, v.last));
+  return __funnelshift_r(lo, hi, (i & 3) * 8);
+}
+// 8 bytes at p; requires p + 8 <= len.
+__device__ __forceinline__ void in_ld8(const InView& v, uint32_t p, uint32_t& lo, uint32_t& hi) {
+  uint32_t i = p + v.mis, k = i >> 2, s = (i & 3) * 8;
+  uint32_t w0 = __ldg(v.w + k), w1 = __ldg(v.w + k + 1), w2 = __ldg(v.w + umin32(k + 2, v.last));
+  lo = __funnelshift_r(w0, w1, s);
+  hi = __funnelshift_r(w1, w2, s);
+}
+__device__ __forceinline__ uint32_t in_byte(const InView& v, uint32_t p) {
+  return __ldg((const uint8_t*)v.w + v.mis + p);
+}
+// common prefix of positions s1 < s2, s2 side bounded by len (uniform result); 128 bytes per step
+__device__ __forceinline__ uint32_t common_prefix_v2(const InView& v, uint32_t len, uint32_t s1, uint32_t s2,
+                                                     uint32_t lane) {
+  uint32_t matched = 0;
+  for (;;) {
+    uint32_t o = 4 * lane, rem = len - s2;
+    uint32_t x;
+    if (rem >= o + 4) {
+      x = in_ld4(v, s1 + o) ^ in_ld4(v, s2 + o);
+    } else {
+      uint32_t nv = rem > o ? rem - o : 0;
+      x = 0;
+      for (uint32_t i = 0; i < nv; i++) x |= (in_byte(v, s1 + o + i) ^ in_byte(v, s2 + o + i)) << (8 * i);
+      x |= 1u << (8 * nv);
+    }
+    uint32_t mism = __ballot_sync(kFull, x != 0);
+    if (mism) {
+      int l = __ffs((int)mism) - 1;
+      uint32_t xl = __shfl_sync(kFull, x, l);
+      return matched + 4 * (uint32_t)l + ((uint32_t)(__ffs((int)xl) - 1) >> 3);
+    }
+    matched += 128; s1 += 128; s2 += 128;
+  }
+}
+__device__ __forceinline__ uint32_t emit_literal_v2(uint8_t* o, const InView& v, uint32_t s, uint32_t n, uint32_t lane) {
+  uint32_t m = (n - 1) & 0xffff, w;
+  if (m < 60) { w = 1; if (lane == 0) o[0] = (uint8_t)(m << 2); }
+  else if (m < 256) { w = 2; if (lane == 0) { o[0] = 60 << 2; o[1] = (uint8_t)m; } }
+  else { w = 3; if (lane == 0) { o[0] = 61 << 2; o[1] = (uint8_t)m; o[2] = (uint8_t)(m >> 8); } }
+  if (n <= 32) {
+    if (lane < n) o[w + lane] = (uint8_t)in_byte(v, s + lane);
+  } else {
+    warp_copy(o + w, (const uint8_t*)v.w + v.mis + s, n, lane);
+  }
+  return w + n;
+}
+__device__ __forceinline__ uint32_t emit_copy_v2(uint8_t* o, uint32_t off, uint32_t len, uint32_t lane) {
+  if (len <= 64) {  // one tag (encoder.nim:113-125)
+    bool c2 = (len >= 12) || (off >= 2048);
+    uint32_t b0 = c2 ? (((len - 1) << 2) | 2) : (((off >> 8) << 5) | ((len - 4) << 2) | 1);
+    if (lane == 0) {
+      o[0] = (uint8_t)b0; o[1] = (uint8_t)off;
+      if (c2) o[2] = (uint8_t)(off >> 8);
+    }
+    return c2 ? 3u : 2u;
+  }
+  return emit_copy_warp(o, off, len, lane);
+}
+
+__device__ __forceinline__ uint32_t compress_block_v2(const uint8_t* __restrict__ in, uint32_t len,
+                                                      uint8_t* __restrict__ out, uint16_t* table,
+                                                      uint32_t abort_thr, uint32_t lane) {
+  InView v;
+  v.mis = (uint32_t)((uintptr_t)in & 3);
+  v.w = (const uint32_t*)(in - v.mis);
+  v.last = (len + v.mis - 1) >> 2;
+  if (len < kMinNonLiteral) return emit_literal_v2(out, v, 0, len, lane);
+
+  uint32_t tsize = 256;
+  while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
+  const uint32_t mask = tsize - 1;
+  {
+    uint32_t* t32 = (uint32_t*)table;
+    for (uint32_t i = lane; i < tsize / 2; i += 32) t32[i] = 0;
+  }
+  const uint32_t ip_limit = len - kInputMargin;
+  const uint32_t below = (1u << lane) - 1u;  // lanes before mine
+  uint32_t op = 0;
+  uint32_t ip = 0;          // chain mode: position of the pending post-copy lookup
+  uint32_t next_emit = 0;   // literal mode: start of the pending literal
+  uint32_t pp = 1;          // literal mode: next probe position
+  uint32_t k = 0;           // literal mode: probes already done in this run
+  bool chain = false;
+
+// finishing sequence shared by every exit: emit in[from..len) and return (encoder.nim:249-253)
+#define SNB_FINISH(from)                                                          \
+  do {                                                                            \
+    uint32_t f_ = (from);                                                         \
+    if (f_ < len) {                                                               \
+      uint32_t n_ = len - f_;                                                     \
+      if (op + literal_size(n_) > abort_thr) return kAborted;                     \
+      op += emit_literal_v2(out + op, v, f_, n_, lane);                           \
+    }                                                                             \
+    return op;                                                                    \
+  } while (0)
+
+  for (;;) {
+    __syncwarp();  // table writes (zeroing / previous commit) visible to every lane
+
+    if (!chain && k >= 32) {
+      // ---- long literal run: strided probes, 32 per step (encoder.nim:311-331 with skip >= 64)
+      uint32_t wip = pp, wskip = 32 + k;
+      uint32_t hit_ip = 0, hit_cand = 0;
+      bool found = false;
+      for (;;) {
+        uint32_t pos = wip, sk = wskip;
+        for (uint32_t j = 0; j < lane; j++) { uint32_t st = sk >> 5; sk += st; pos += st; }
+        uint32_t step = sk >> 5, sk_after = sk + step;
+        bool valid = (pos <= ip_limit) && (pos + step <= ip_limit);
+        uint32_t d = 0, h = 0x10000u + lane, tv = 0;
+        if (valid) { d = in_ld4(v, pos); h = hash14(d, mask); tv = table[h]; }
+        uint32_t grp = __match_any_sync(kFull, h);
+        uint32_t earlier = grp & below;
+        int src = earlier ? 31 - __clz((int)earlier) : (int)lane;
+        uint32_t pe = __shfl_sync(kFull, pos, src);
+        uint32_t c = earlier ? pe : tv;
+        bool hit = valid && (in_ld4(v, c) == d);
+        uint32_t hitmask = __ballot_sync(kFull, hit);
+        uint32_t vmask = __ballot_sync(kFull, valid);
+        if (hitmask) {
+          int kh = __ffs((int)hitmask) - 1;
+          uint32_t commit = (2u << kh) - 1u;
+          if (((commit >> lane) & 1u) && ((grp & commit) >> lane) == 1u) table[h] = (uint16_t)pos;
+          hit_ip = __shfl_sync(kFull, pos, kh);
+          hit_cand = __shfl_sync(kFull, c, kh);
+          found = true;
+          break;
+        }
+        if (vmask != kFull) break;
+        if ((grp >> lane) == 1u) table[h] = (uint16_t)pos;
+        wip = __shfl_sync(kFull, pos + step, 31);
+        wskip = __shfl_sync(kFull, sk_after, 31);
+        __syncwarp();
+      }
+      if (!found) SNB_FINISH(next_emit);
+      {
+        uint32_t n = hit_ip - next_emit;
+        if (op + literal_size(n) > abort_thr) return kAborted;
+        op += emit_literal_v2(out + op, v, next_emit, n, lane);
+      }
+      uint32_t m = 4 + common_prefix_v2(v, len, hit_cand + 4, hit_ip + 4, lane);
+      op += emit_copy_v2(out + op, hit_ip - hit_cand, m, lane);
+      ip = hit_ip + m;
+      if (op > abort_thr) return kAborted;
+      if (ip > ip_limit) SNB_FINISH(ip);
+      chain = true;
+      continue;
+    }
+
+    // ---- phase A
+    const uint32_t b = chain ? ip - 1 : pp;
+    const uint32_t p = b + lane;
+    uint32_t h = 0x10000u + lane, T = 0, ml = 0;
+    if (p <= ip_limit) {
+      uint32_t a_lo, a_hi, c_lo, c_hi;
+      in_ld8(v, p, a_lo, a_hi);
+      h = hash14(a_lo, mask);
+      T = table[h];
+      in_ld8(v, T, c_lo, c_hi);
+      uint32_t x_lo = a_lo ^ c_lo, x_hi = a_hi ^ c_hi;
+      ml = x_lo ? ((uint32_t)(__ffs((int)x_lo) - 1) >> 3) : (x_hi ? 4 + ((uint32_t)(__ffs((int)x_hi) - 1) >> 3) : 8);
+    }
+    const uint32_t grp = __match_any_sync(kFull, h);
+    const uint32_t pk = T | (ml << 16);
+    uint32_t ins = 0;
+
+    // ---- phase B
+    for (;;) {
+      uint32_t l, cand, m;
+      if (chain) {
+        l = ip - b;
+        if (l >= 32) break;
+        ins |= 1u << (l - 1);                                   // encoder.nim:371 insert ip-1
+        uint32_t g = __shfl_sync(kFull, grp, (int)l);
+        uint32_t q = __shfl_sync(kFull, pk, (int)l);
+        uint32_t st = g & ins;                                  // same-hash positions inserted in this window
+        ins |= 1u << l;                                         // :373-377 look up, then insert ip
+        if (st) {
+          cand = b + (uint32_t)(31 - __clz((int)st));
+          m = common_prefix_v2(v, len, cand, ip, lane);
+        } else {
+          cand = q & 0xffff;
+          m = q >> 16;
+          if (m == 8) m = 8 + common_prefix_v2(v, len, cand + 8, ip + 8, lane);
+        }
+        if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }   // :379-380
+      } else {
+        uint32_t l0 = pp - b;
+        if (l0 >= 32) break;
+        uint32_t lmax = l0 + (32 - k);                          // stride-1 probes end when k reaches 32
+        bool pv = lane >= l0 && lane < lmax && p + 1 <= ip_limit;  // :318-321
+        uint32_t before = below & ~((1u << l0) - 1u);            // probes of this run before mine
+        bool stale = pv && (grp & (ins | before)) != 0;
+        bool hit = pv && !stale && ml >= 4;
+        uint32_t ev = __ballot_sync(kFull, hit || stale);
+        uint32_t vm = __ballot_sync(kFull, pv);
+        uint32_t from_l0 = ~((1u << l0) - 1u);
+        uint32_t inval = ~vm & from_l0;
+        uint32_t end_lane = inval ? (uint32_t)(__ffs((int)inval) - 1) : 32u;
+        uint32_t e = ev ? (uint32_t)(__ffs((int)ev) - 1) : 32u;
+        if (e >= end_lane) {                                     // every probe up to end_lane missed
+          if (end_lane > l0) ins |= (end_lane >= 32 ? 0xffffffffu : ((1u << end_lane) - 1u)) & from_l0;
+          k += end_lane - l0;
+          pp = b + end_lane;
+          if (end_lane < 32 && k < 32) SNB_FINISH(next_emit);    // ran into ip_limit (:319-321)
+          break;                                                 // window exhausted, or k == 32
+        }
+        if (e > l0) ins |= ((1u << e) - 1u) & from_l0;           // probes before e inserted, no hit
+        uint32_t g = __shfl_sync(kFull, grp, (int)e);
+        uint32_t q = __shfl_sync(kFull, pk, (int)e);
+        uint32_t st = g & ins;
+        ins |= 1u << e;                                          // :293-294 insert before comparing
+        l = e;
+        if (st) {
+          cand = b + (uint32_t)(31 - __clz((int)st));
+          m = common_prefix_v2(v, len, cand, b + e, lane);
+          if (m < 4) { k += e + 1 - l0; pp = b + e + 1; continue; }
+        } else {
+          cand = q & 0xffff;
+          m = q >> 16;
+          if (m == 8) m = 8 + common_prefix_v2(v, len, cand + 8, b + e + 8, lane);
+        }
+        ip = b + e;
+        uint32_t n = ip - next_emit;                             // :336-338
+        if (op + literal_size(n) > abort_thr) return kAborted;
+        op += emit_literal_v2(out + op, v, next_emit, n, lane);
+        chain = true;
+      }
+      // ---- emit the copy found at ip against cand (:356-363)
+      op += emit_copy_v2(out + op, ip - cand, m, lane);
+      ip += m;
+      if (op > abort_thr) return kAborted;
+      if (ip > ip_limit) SNB_FINISH(ip);
+    }
+
+    // ---- commit the window's inserts (last inserted lane of each hash group wins)
+    if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[h] = (uint16_t)p;
+  }
+#undef SNB_FINISH
+}
+
 struct CompressArgs {
   const uint8_t* in_base;
   uint8_t* out_base;
@@ -348,6 +618,7 @@ struct CompressArgs {
   uint32_t count;
   uint32_t mode;
   uint32_t table_entries;   // per-warp shared-memory table capacity (u16 entries)
+  uint32_t algo;            // 1: compress_block_warp (v1), otherwise compress_block_v2
 };
 
 __device__ __forceinline__ uint32_t put_varint32(uint8_t* o, uint32_t v, uint32_t lane) {
@@ -358,6 +629,12 @@ __device__ __forceinline__ uint32_t put_varint32(uint8_t* o, uint32_t v, uint32_
 }
 __device__ __forceinline__ uint32_t varint32_len(uint32_t v) {
   return v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5;
+}
+
+__device__ __forceinline__ uint32_t encode_block(uint32_t algo, const uint8_t* in, uint32_t len, uint8_t* out,
+                                                 uint16_t* table, uint32_t abort_thr, uint32_t lane) {
+  if (algo == 1) return compress_block_warp(in, len, out, table, abort_thr, lane);
+  return compress_block_v2(in, len, out, table, abort_thr, lane);
 }
 
 // One job = one encodeFrame (encoder.nim:385-426), one bare encodeBlock, or one whole
@@ -374,7 +651,7 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
     uint32_t hl = varint32_len(len);
     uint32_t thr = len - len / 8;
     uint32_t bl = kAborted;
-    if (len >= kMinNonLiteral) bl = compress_block_warp(in, len, out + 8 + hl, table, thr, lane);  // :401-406
+    if (len >= kMinNonLiteral) bl = encode_block(a.algo, in, len, out + 8 + hl, table, thr, lane);  // :401-406
     uint32_t fl;
     if (bl != kAborted && bl <= thr) {  // :408-416
       put_varint32(out + 8, len, lane);
@@ -391,10 +668,10 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
     }
     total = fl + 4;
   } else if (a.mode == kModeRawBlock) {
-    total = len ? compress_block_warp(in, len, out, table, kNoAbort, lane) : 0;
+    total = len ? encode_block(a.algo, in, len, out, table, kNoAbort, lane) : 0;
   } else {
     uint32_t hl = put_varint32(out, len, lane);
-    total = hl + (len ? compress_block_warp(in, len, out + hl, table, kNoAbort, lane) : 0);
+    total = hl + (len ? encode_block(a.algo, in, len, out + hl, table, kNoAbort, lane) : 0);
   }
   if (lane == 0) a.out_len[job] = total;
 }
