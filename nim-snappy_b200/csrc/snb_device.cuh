@@ -458,6 +458,15 @@ __device__ __forceinline__ uint32_t compress_block_v2(const uint8_t* __restrict_
     }                                                                             \
     return op;                                                                    \
   } while (0)
+// deferred write of this window's simple copy tags (each lane wrote down its offset in myoff)
+#define SNB_FLUSH_TAGS()                                                          \
+  do {                                                                            \
+    if ((copymask >> lane) & 1u) {                                                \
+      uint8_t* o_ = out + myoff;                                                  \
+      o_[0] = (uint8_t)tagw; o_[1] = (uint8_t)(tagw >> 8);                        \
+      if (tagw >> 24) o_[2] = (uint8_t)(tagw >> 16);                              \
+    }                                                                             \
+  } while (0)
 
   for (;;) {
     __syncwarp();  // table writes (zeroing / previous commit) visible to every lane
@@ -512,95 +521,117 @@ __device__ __forceinline__ uint32_t compress_block_v2(const uint8_t* __restrict_
       continue;
     }
 
-    // ---- phase A
+    // ---- phase A: per-lane lookup against the table as of the window start
     const uint32_t b = chain ? ip - 1 : pp;
     const uint32_t p = b + lane;
-    uint32_t h = 0x10000u + lane, T = 0, ml = 0;
+    uint32_t h = 0x10000u + lane, rec = 0, tagw = 0;
     if (p <= ip_limit) {
       uint32_t a_lo, a_hi, c_lo, c_hi;
       in_ld8(v, p, a_lo, a_hi);
       h = hash14(a_lo, mask);
-      T = table[h];
+      uint32_t T = table[h];
       in_ld8(v, T, c_lo, c_hi);
       uint32_t x_lo = a_lo ^ c_lo, x_hi = a_hi ^ c_hi;
-      ml = x_lo ? ((uint32_t)(__ffs((int)x_lo) - 1) >> 3) : (x_hi ? 4 + ((uint32_t)(__ffs((int)x_hi) - 1) >> 3) : 8);
+      uint32_t ml = x_lo ? ((uint32_t)(__ffs((int)x_lo) - 1) >> 3) : (x_hi ? 4 + ((uint32_t)(__ffs((int)x_hi) - 1) >> 3) : 8);
+      // the copy tag a 4..7-byte match at this position would emit (encoder.nim:113-125)
+      uint32_t off = p - T;
+      bool c2 = off >= 2048;
+      uint32_t t0 = c2 ? (((ml - 1) << 2) | 2) : (((off >> 8) << 5) | ((ml - 4) << 2) | 1);
+      tagw = (t0 & 0xff) | ((off & 0xff) << 8) | (c2 ? (((off >> 8) & 0xff) << 16) | (1u << 24) : 0u);
+      rec = T | (ml << 16) | ((c2 ? 3u : 2u) << 24);
     }
     const uint32_t grp = __match_any_sync(kFull, h);
-    const uint32_t pk = T | (ml << 16);
-    uint32_t ins = 0;
+    uint32_t ins = 0, copymask = 0, myoff = 0;
 
-    // ---- phase B
+    // ---- phase B: walk the parse through the window
     for (;;) {
-      uint32_t l, cand, m;
+      uint32_t cand, m;
       if (chain) {
-        l = ip - b;
+        const uint32_t l = ip - b;
         if (l >= 32) break;
-        ins |= 1u << (l - 1);                                   // encoder.nim:371 insert ip-1
-        uint32_t g = __shfl_sync(kFull, grp, (int)l);
-        uint32_t q = __shfl_sync(kFull, pk, (int)l);
-        uint32_t st = g & ins;                                  // same-hash positions inserted in this window
-        ins |= 1u << l;                                         // :373-377 look up, then insert ip
+        const uint32_t bl1 = 1u << (l - 1);
+        const uint32_t g = __shfl_sync(kFull, grp, (int)l);
+        const uint32_t q = __shfl_sync(kFull, rec, (int)l);
+        const uint32_t st = g & (ins | bl1);                    // same-hash positions inserted in this window
+        ins |= bl1 | (bl1 << 1);                                // encoder.nim:371-377: insert ip-1, look up + insert ip
+        m = (q >> 16) & 0xff;
+        if (st == 0 && m < 8) {
+          if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }   // :379-380
+          if (lane == l) myoff = op;                            // simple copy: tag written at window end
+          copymask |= bl1 << 1;
+          op += q >> 24;
+          ip += m;
+          if (ip > ip_limit) { SNB_FLUSH_TAGS(); if (op > abort_thr) return kAborted; SNB_FINISH(ip); }
+          continue;
+        }
         if (st) {
           cand = b + (uint32_t)(31 - __clz((int)st));
           m = common_prefix_v2(v, len, cand, ip, lane);
+          if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }
         } else {
           cand = q & 0xffff;
-          m = q >> 16;
-          if (m == 8) m = 8 + common_prefix_v2(v, len, cand + 8, ip + 8, lane);
+          m = 8 + common_prefix_v2(v, len, cand + 8, ip + 8, lane);
         }
-        if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }   // :379-380
       } else {
-        uint32_t l0 = pp - b;
+        const uint32_t l0 = pp - b;
         if (l0 >= 32) break;
-        uint32_t lmax = l0 + (32 - k);                          // stride-1 probes end when k reaches 32
-        bool pv = lane >= l0 && lane < lmax && p + 1 <= ip_limit;  // :318-321
-        uint32_t before = below & ~((1u << l0) - 1u);            // probes of this run before mine
-        bool stale = pv && (grp & (ins | before)) != 0;
-        bool hit = pv && !stale && ml >= 4;
-        uint32_t ev = __ballot_sync(kFull, hit || stale);
-        uint32_t vm = __ballot_sync(kFull, pv);
-        uint32_t from_l0 = ~((1u << l0) - 1u);
-        uint32_t inval = ~vm & from_l0;
-        uint32_t end_lane = inval ? (uint32_t)(__ffs((int)inval) - 1) : 32u;
-        uint32_t e = ev ? (uint32_t)(__ffs((int)ev) - 1) : 32u;
+        const uint32_t lmax = l0 + (32 - k);                    // stride-1 probes end when k reaches 32
+        const bool pv = lane >= l0 && lane < lmax && p + 1 <= ip_limit;  // :318-321
+        const uint32_t from_l0 = ~((1u << l0) - 1u);
+        const bool stale = pv && (grp & (ins | (below & from_l0))) != 0;
+        const bool hit = pv && !stale && ((rec >> 16) & 0xff) >= 4;
+        const uint32_t ev = __ballot_sync(kFull, hit || stale);
+        const uint32_t vm = __ballot_sync(kFull, pv);
+        const uint32_t inval = ~vm & from_l0;
+        const uint32_t end_lane = inval ? (uint32_t)(__ffs((int)inval) - 1) : 32u;
+        const uint32_t e = ev ? (uint32_t)(__ffs((int)ev) - 1) : 32u;
         if (e >= end_lane) {                                     // every probe up to end_lane missed
           if (end_lane > l0) ins |= (end_lane >= 32 ? 0xffffffffu : ((1u << end_lane) - 1u)) & from_l0;
           k += end_lane - l0;
           pp = b + end_lane;
-          if (end_lane < 32 && k < 32) SNB_FINISH(next_emit);    // ran into ip_limit (:319-321)
+          if (end_lane < 32 && k < 32) { SNB_FLUSH_TAGS(); if (op > abort_thr) return kAborted; SNB_FINISH(next_emit); }
           break;                                                 // window exhausted, or k == 32
         }
         if (e > l0) ins |= ((1u << e) - 1u) & from_l0;           // probes before e inserted, no hit
-        uint32_t g = __shfl_sync(kFull, grp, (int)e);
-        uint32_t q = __shfl_sync(kFull, pk, (int)e);
-        uint32_t st = g & ins;
+        const uint32_t g = __shfl_sync(kFull, grp, (int)e);
+        const uint32_t q = __shfl_sync(kFull, rec, (int)e);
+        const uint32_t st = g & ins;
         ins |= 1u << e;                                          // :293-294 insert before comparing
-        l = e;
+        m = (q >> 16) & 0xff;
+        cand = q & 0xffff;
         if (st) {
           cand = b + (uint32_t)(31 - __clz((int)st));
           m = common_prefix_v2(v, len, cand, b + e, lane);
           if (m < 4) { k += e + 1 - l0; pp = b + e + 1; continue; }
-        } else {
-          cand = q & 0xffff;
-          m = q >> 16;
-          if (m == 8) m = 8 + common_prefix_v2(v, len, cand + 8, b + e + 8, lane);
         }
         ip = b + e;
-        uint32_t n = ip - next_emit;                             // :336-338
+        const uint32_t n = ip - next_emit;                       // :336-338
         if (op + literal_size(n) > abort_thr) return kAborted;
         op += emit_literal_v2(out + op, v, next_emit, n, lane);
         chain = true;
+        if (st == 0 && m < 8) {                                  // simple copy at lane e
+          if (lane == e) myoff = op;
+          copymask |= 1u << e;
+          op += q >> 24;
+          ip += m;
+          if (ip > ip_limit) { SNB_FLUSH_TAGS(); if (op > abort_thr) return kAborted; SNB_FINISH(ip); }
+          continue;
+        }
+        if (st == 0) m = 8 + common_prefix_v2(v, len, cand + 8, ip + 8, lane);
       }
-      // ---- emit the copy found at ip against cand (:356-363)
+      // ---- general copy at ip against cand (:356-363): long, re-measured or many-tag copies
       op += emit_copy_v2(out + op, ip - cand, m, lane);
       ip += m;
-      if (op > abort_thr) return kAborted;
-      if (ip > ip_limit) SNB_FINISH(ip);
+      if (ip > ip_limit) { SNB_FLUSH_TAGS(); if (op > abort_thr) return kAborted; SNB_FINISH(ip); }
     }
 
-    // ---- commit the window's inserts (last inserted lane of each hash group wins)
+    // ---- window end: write the deferred copy tags, commit the inserts (last inserted lane of
+    // each hash group wins), bound the output
+    SNB_FLUSH_TAGS();
     if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[h] = (uint16_t)p;
+    if (op > abort_thr) return kAborted;
   }
+#undef SNB_FLUSH_TAGS
 #undef SNB_FINISH
 }
 
