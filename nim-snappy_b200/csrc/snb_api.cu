@@ -84,7 +84,7 @@ struct Ctx {
   float prof[6] = {0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
   uint32_t call_launches = 0;
-  int compress_warps = 6;
+  int compress_warps = 7;
   int compress_algo = 2;
   std::string err;
 };

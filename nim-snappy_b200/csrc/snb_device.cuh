@@ -397,6 +397,24 @@ __device__ __forceinline__ uint32_t common_prefix_v2(const InView& v, uint32_t l
     matched += 128; s1 += 128; s2 += 128;
   }
 }
+// Extension of a match known to be equal up to s1/s2: two uniform 8-byte steps (most matches
+// end within them), then the 128-byte-per-step warp compare.
+__device__ __forceinline__ uint32_t extend_match_v2(const InView& v, uint32_t len, uint32_t s1, uint32_t s2,
+                                                    uint32_t lane) {
+  uint32_t m = 0;
+#pragma unroll 1
+  for (int it = 0; it < 2 && s2 + m + 8 <= len; it++) {
+    uint32_t a_lo, a_hi, b_lo, b_hi;
+    in_ld8(v, s1 + m, a_lo, a_hi);
+    in_ld8(v, s2 + m, b_lo, b_hi);
+    uint32_t x_lo = a_lo ^ b_lo, x_hi = a_hi ^ b_hi;
+    if (x_lo) return m + ((uint32_t)(__ffs((int)x_lo) - 1) >> 3);
+    if (x_hi) return m + 4 + ((uint32_t)(__ffs((int)x_hi) - 1) >> 3);
+    m += 8;
+  }
+  return m + common_prefix_v2(v, len, s1 + m, s2 + m, lane);
+}
+
 __device__ __forceinline__ uint32_t emit_literal_v2(uint8_t* o, const InView& v, uint32_t s, uint32_t n, uint32_t lane) {
   uint32_t m = (n - 1) & 0xffff, w;
   if (m < 60) { w = 1; if (lane == 0) o[0] = (uint8_t)(m << 2); }
@@ -541,6 +559,9 @@ __device__ __forceinline__ uint32_t compress_block_v2(const uint8_t* __restrict_
       rec = T | (ml << 16) | ((c2 ? 3u : 2u) << 24);
     }
     const uint32_t grp = __match_any_sync(kFull, h);
+    const uint32_t eg = grp & below;                             // earlier lanes of my hash group
+    const uint32_t hitbits = __ballot_sync(kFull, ((rec >> 16) & 0xff) >= 4);
+    const uint32_t lim_lane = ip_limit > b ? ip_limit - b : 0;   // probes need p + 1 <= ip_limit (:318-321)
     uint32_t ins = 0, copymask = 0, myoff = 0;
 
     // ---- phase B: walk the parse through the window
@@ -570,20 +591,18 @@ __device__ __forceinline__ uint32_t compress_block_v2(const uint8_t* __restrict_
           if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }
         } else {
           cand = q & 0xffff;
-          m = 8 + common_prefix_v2(v, len, cand + 8, ip + 8, lane);
+          m = 8 + extend_match_v2(v, len, cand + 8, ip + 8, lane);
         }
       } else {
         const uint32_t l0 = pp - b;
         if (l0 >= 32) break;
-        const uint32_t lmax = l0 + (32 - k);                    // stride-1 probes end when k reaches 32
-        const bool pv = lane >= l0 && lane < lmax && p + 1 <= ip_limit;  // :318-321
-        const uint32_t from_l0 = ~((1u << l0) - 1u);
-        const bool stale = pv && (grp & (ins | (below & from_l0))) != 0;
-        const bool hit = pv && !stale && ((rec >> 16) & 0xff) >= 4;
-        const uint32_t ev = __ballot_sync(kFull, hit || stale);
-        const uint32_t vm = __ballot_sync(kFull, pv);
-        const uint32_t inval = ~vm & from_l0;
-        const uint32_t end_lane = inval ? (uint32_t)(__ffs((int)inval) - 1) : 32u;
+        const uint32_t from_l0 = 0xffffffffu << l0;
+        // probe lanes of this run inside the window: stride 1 until k reaches 32, and p + 1 <= ip_limit
+        const uint32_t hi = umax32(l0, umin32(umin32(32u, l0 + (32 - k)), lim_lane));
+        const uint32_t range = from_l0 & (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u));
+        const uint32_t sm = __ballot_sync(kFull, (eg & (ins | from_l0)) != 0);   // stale: same hash inserted before me
+        const uint32_t ev = (hitbits | sm) & range;
+        const uint32_t end_lane = hi;
         const uint32_t e = ev ? (uint32_t)(__ffs((int)ev) - 1) : 32u;
         if (e >= end_lane) {                                     // every probe up to end_lane missed
           if (end_lane > l0) ins |= (end_lane >= 32 ? 0xffffffffu : ((1u << end_lane) - 1u)) & from_l0;
@@ -617,7 +636,7 @@ __device__ __forceinline__ uint32_t compress_block_v2(const uint8_t* __restrict_
           if (ip > ip_limit) { SNB_FLUSH_TAGS(); if (op > abort_thr) return kAborted; SNB_FINISH(ip); }
           continue;
         }
-        if (st == 0) m = 8 + common_prefix_v2(v, len, cand + 8, ip + 8, lane);
+        if (st == 0) m = 8 + extend_match_v2(v, len, cand + 8, ip + 8, lane);
       }
       // ---- general copy at ip against cand (:356-363): long, re-measured or many-tag copies
       op += emit_copy_v2(out + op, ip - cand, m, lane);
