@@ -138,8 +138,11 @@ int snb_get_profile(float *ms, int n);
 uint64_t snb_kernel_launches(void);
 /* Tuning: warps per CTA of the compress kernel for 64 KiB blocks (hash tables are 32 KiB each). */
 void snb_set_compress_warps(int warps);
-/* Tuning / A-B testing: 1 = per-step warp encoder (v1), 2 = window-resolve encoder (default). */
+/* Tuning / A-B testing of the block encoder: 0 = auto (default: one thread per block with tables in HBM for
+ * batches of at least `thread_min_chunks` blocks, window-resolve warps otherwise), 1 = per-step warp encoder,
+ * 2 = window-resolve warp encoder, 3 = one thread per block. */
 void snb_set_compress_algo(int algo);
+void snb_set_thread_min_chunks(int n);
 
 #ifdef __cplusplus
 }

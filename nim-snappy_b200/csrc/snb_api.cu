@@ -76,7 +76,7 @@ struct Ctx {
   uint32_t* d_counters = nullptr;
   int counter_next = 0;
   uint64_t* d_total = nullptr;  // 4 device scalars
-  DevBuf scratch, lens, offs, crcs, chunks, status, outlen, in[2], out[2];
+  DevBuf scratch, lens, offs, crcs, chunks, status, outlen, tables, in[2], out[2];
   PinBuf h_in[2], h_out[2], h_meta[2];
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   cudaEvent_t ev_prof[12] = {};
@@ -85,7 +85,8 @@ struct Ctx {
   uint64_t launches = 0;
   uint32_t call_launches = 0;
   int compress_warps = 7;
-  int compress_algo = 2;
+  int compress_algo = 0;  // 0 auto (thread-per-block for big batches, else window-resolve warps), 1/2 warp v1/v2, 3 thread
+  int thread_min_chunks = 4096;  // batches at least this large use one thread per block (tables in HBM)
   std::string err;
 };
 Ctx g;
@@ -288,16 +289,29 @@ int dev_compress_contig(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
       CKS(launch_crc(sin, nullptr, nullptr, slen, cnt, g.crcs.as<uint32_t>(), 1, st));
       if (p) prof_mark(1, st);
     }
-    snb::CompressArgs a;
-    a.in_base = sin; a.out_base = g.scratch.as<uint8_t>(); a.in_off = nullptr; a.in_len = nullptr; a.out_off = nullptr;
-    a.total_len = slen; a.out_stride = kSlotStride; a.crc = g.crcs.as<uint32_t>(); a.out_len = g.lens.as<uint32_t>();
-    a.count = cnt; a.mode = mode;
-    CKS(next_counter(st, &a.counter));
-    CompressGeom cg = compress_geom((uint32_t)kChunk, cnt);
-    a.table_entries = cg.entries;
-    a.algo = (uint32_t)g.compress_algo;
-    if (p) prof_mark(2, st);
-    SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
+    if (g.compress_algo != 1 && g.compress_algo != 2 && cnt >= (uint32_t)g.thread_min_chunks || g.compress_algo == 3) {
+      // one thread per block, hash tables in global memory
+      CK(g.tables.ensure((size_t)cnt * snb::kMaxTableEntries * 2));
+      CK(cudaMemsetAsync(g.tables.p, 0, (size_t)cnt * snb::kMaxTableEntries * 2, st));
+      snb::CompressTArgs t;
+      t.in_base = sin; t.out_base = g.scratch.as<uint8_t>(); t.tables = g.tables.as<uint16_t>(); t.total_len = slen;
+      t.out_stride = kSlotStride; t.crc = g.crcs.as<uint32_t>(); t.out_len = g.lens.as<uint32_t>(); t.count = cnt;
+      t.mode = mode;
+      if (p) prof_mark(2, st);
+      SNB_LAUNCH(snb::compress_thread_kernel, (cnt + 31) / 32, 32, 0, st, t);
+    } else {
+      snb::CompressArgs a;
+      a.in_base = sin; a.out_base = g.scratch.as<uint8_t>(); a.in_off = nullptr; a.in_len = nullptr; a.out_off = nullptr;
+      a.total_len = slen; a.out_stride = kSlotStride; a.crc = g.crcs.as<uint32_t>(); a.out_len = g.lens.as<uint32_t>();
+      a.count = cnt; a.mode = mode;
+      CKS(next_counter(st, &a.counter));
+      CompressGeom cg = compress_geom((uint32_t)kChunk, cnt);
+      a.table_entries = cg.entries;
+      a.algo = (uint32_t)g.compress_algo;
+      a.defer_stored = mode == snb::kModeFrame ? 1u : 0u;
+      if (p) prof_mark(2, st);
+      SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
+    }
     count_launch();
     CK(cudaGetLastError());
     if (p) { prof_mark(3, st); prof_mark(4, st); }
@@ -309,7 +323,7 @@ int dev_compress_contig(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
     if (p) { prof_mark(5, st); prof_mark(6, st); }
     uint32_t cgrid = std::max(1u, std::min(cnt, (uint32_t)g.sms * 8));
     SNB_LAUNCH(snb::compact_kernel, cgrid, 256, 0, st, g.scratch.as<uint8_t>(), kSlotStride, g.lens.as<uint32_t>(),
-               g.offs.as<uint64_t>(), d_dst, cnt);
+               g.offs.as<uint64_t>(), d_dst, cnt, mode == snb::kModeFrame ? sin : (const uint8_t*)nullptr);
     count_launch();
     CK(cudaGetLastError());
     if (p) prof_mark(7, st);
@@ -592,7 +606,7 @@ void snb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.ready) return;
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.in[0], &g.in[1], &g.out[0], &g.out[1]})
+  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.tables, &g.in[0], &g.in[1], &g.out[0], &g.out[1]})
     b->release();
   for (PinBuf* b : {&g.h_in[0], &g.h_in[1], &g.h_out[0], &g.h_out[1], &g.h_meta[0], &g.h_meta[1]}) b->release();
   cudaFree(g.d_tables); cudaFree(g.d_hdr); cudaFree(g.d_counters); cudaFree(g.d_total);
@@ -803,7 +817,8 @@ int snb_dev_compress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const 
   CKS(next_counter(st, &a.counter));
   CompressGeom cg = compress_geom(max_len, (uint32_t)count);
   a.table_entries = cg.entries;
-  a.algo = (uint32_t)g.compress_algo;
+  a.algo = (uint32_t)(g.compress_algo == 1 ? 1 : 2);
+  a.defer_stored = 0;
   prof_mark(2, st);
   SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
   count_launch();
@@ -870,5 +885,6 @@ int snb_get_profile(float* ms, int n) {
 uint64_t snb_kernel_launches(void) { return g.launches; }
 void snb_set_compress_warps(int warps) { g.compress_warps = warps; }
 void snb_set_compress_algo(int algo) { g.compress_algo = algo; }
+void snb_set_thread_min_chunks(int n) { g.thread_min_chunks = n; }
 
 }  // extern "C"

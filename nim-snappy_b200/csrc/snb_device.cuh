@@ -669,6 +669,7 @@ struct CompressArgs {
   uint32_t mode;
   uint32_t table_entries;   // per-warp shared-memory table capacity (u16 entries)
   uint32_t algo;            // 1: compress_block_warp (v1), otherwise compress_block_v2
+  uint32_t defer_stored;    // 1: stored frames get only their header here (compact_kernel copies the payload)
 };
 
 __device__ __forceinline__ uint32_t put_varint32(uint8_t* o, uint32_t v, uint32_t lane) {
@@ -710,7 +711,7 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
     } else {  // :418-426
       fl = len + 4;
       if (lane == 0) out[0] = 0x01;
-      warp_copy(out + 8, in, len, lane);
+      if (!a.defer_stored) warp_copy(out + 8, in, len, lane);
     }
     if (lane == 0) {
       out[1] = (uint8_t)fl; out[2] = (uint8_t)(fl >> 8); out[3] = (uint8_t)(fl >> 16);
@@ -740,6 +741,158 @@ __global__ void __launch_bounds__(256) compress_kernel(CompressArgs a) {
     compress_job(a, job, table, lane);
     __syncwarp();
   }
+}
+
+// --------------------------------------------------------------------- encodeBlock, one THREAD per block
+// For large batches the serial chain is better hidden by running every block at once: one
+// thread per 64 KiB block, hash table in global memory (32 KiB per thread, zeroed by the host),
+// the reference's loop verbatim (encoder.nim:184-383).  Tens of thousands of independent
+// dependent-load chains keep HBM busy; the warp-cooperative kernel above wins only when the
+// batch is too small to fill the machine this way.
+__device__ __forceinline__ uint32_t thread_emit_literal(uint8_t* o, const InView& v, uint32_t s, uint32_t n) {
+  uint32_t m = (n - 1) & 0xffff, w;
+  if (m < 60) { o[0] = (uint8_t)(m << 2); w = 1; }
+  else if (m < 256) { o[0] = 60 << 2; o[1] = (uint8_t)m; w = 2; }
+  else { o[0] = 61 << 2; o[1] = (uint8_t)m; o[2] = (uint8_t)(m >> 8); w = 3; }
+  const uint8_t* src = (const uint8_t*)v.w + v.mis + s;
+  for (uint32_t i = 0; i < n; i++) o[w + i] = __ldg(src + i);
+  return w + n;
+}
+__device__ __forceinline__ uint32_t thread_emit_copy(uint8_t* o, uint32_t off, uint32_t len) {
+  uint32_t w = 0;
+  while (len >= 68) { o[w] = (63 << 2) | 2; o[w + 1] = (uint8_t)off; o[w + 2] = (uint8_t)(off >> 8); w += 3; len -= 64; }
+  if (len > 64) { o[w] = (59 << 2) | 2; o[w + 1] = (uint8_t)off; o[w + 2] = (uint8_t)(off >> 8); w += 3; len -= 60; }
+  if (len >= 12 || off >= 2048) {
+    o[w] = (uint8_t)(((len - 1) << 2) | 2); o[w + 1] = (uint8_t)off; o[w + 2] = (uint8_t)(off >> 8);
+    return w + 3;
+  }
+  o[w] = (uint8_t)(((off >> 8) << 5) | ((len - 4) << 2) | 1);
+  o[w + 1] = (uint8_t)off;
+  return w + 2;
+}
+// longest common prefix of positions s1 < s2, s2 side bounded by len (encoder.nim:130-182)
+__device__ __forceinline__ uint32_t thread_match_len(const InView& v, uint32_t len, uint32_t s1, uint32_t s2) {
+  uint32_t m = 0;
+  while (s2 + m + 8 <= len) {
+    uint32_t a_lo, a_hi, b_lo, b_hi;
+    in_ld8(v, s1 + m, a_lo, a_hi);
+    in_ld8(v, s2 + m, b_lo, b_hi);
+    uint32_t x_lo = a_lo ^ b_lo, x_hi = a_hi ^ b_hi;
+    if (x_lo) return m + ((uint32_t)(__ffs((int)x_lo) - 1) >> 3);
+    if (x_hi) return m + 4 + ((uint32_t)(__ffs((int)x_hi) - 1) >> 3);
+    m += 8;
+  }
+  while (s2 + m < len && in_byte(v, s1 + m) == in_byte(v, s2 + m)) m++;
+  return m;
+}
+__device__ __forceinline__ uint32_t compress_block_thread(const uint8_t* __restrict__ in, uint32_t len,
+                                                          uint8_t* __restrict__ out, uint16_t* __restrict__ table,
+                                                          uint32_t abort_thr) {
+  InView v;
+  v.mis = (uint32_t)((uintptr_t)in & 3);
+  v.w = (const uint32_t*)(in - v.mis);
+  v.last = (len + v.mis - 1) >> 2;
+  if (len < kMinNonLiteral) return thread_emit_literal(out, v, 0, len);
+  uint32_t tsize = 256;
+  while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
+  const uint32_t mask = tsize - 1;
+  const uint32_t ip_limit = len - kInputMargin;
+  uint32_t ip = 0, op = 0;
+  for (;;) {
+    uint32_t next_emit = ip++;
+    uint32_t skip = 32, cand = 0;
+    bool found = false;
+    // encoder.nim:281-331; the 16 unrolled probes and the scan loop are the same per-probe step once
+    // "a probe happens only if ip + (skip >> 5) <= ip_limit" is applied uniformly (see compress_block_warp)
+    for (;;) {
+      uint32_t step = skip >> 5;
+      skip += step;
+      uint32_t next_ip = ip + step;
+      if (next_ip > ip_limit) break;
+      uint32_t d = in_ld4(v, ip), h = hash14(d, mask);
+      cand = table[h];
+      table[h] = (uint16_t)ip;
+      if (in_ld4(v, cand) == d) { found = true; break; }
+      ip = next_ip;
+    }
+    if (!found) {
+      uint32_t n = len - next_emit;
+      if (op + literal_size(n) > abort_thr) return kAborted;
+      return op + thread_emit_literal(out + op, v, next_emit, n);
+    }
+    {
+      uint32_t n = ip - next_emit;
+      if (op + literal_size(n) > abort_thr) return kAborted;
+      op += thread_emit_literal(out + op, v, next_emit, n);
+    }
+    for (;;) {
+      uint32_t matched = 4 + thread_match_len(v, len, cand + 4, ip + 4);
+      op += thread_emit_copy(out + op, ip - cand, matched);
+      ip += matched;
+      if (op > abort_thr) return kAborted;
+      if (ip > ip_limit) {
+        if (ip < len) {
+          uint32_t n = len - ip;
+          if (op + literal_size(n) > abort_thr) return kAborted;
+          op += thread_emit_literal(out + op, v, ip, n);
+        }
+        return op;
+      }
+      uint32_t d1, dhi;
+      in_ld8(v, ip - 1, d1, dhi);
+      uint32_t d = __funnelshift_r(d1, dhi, 8);
+      table[hash14(d1, mask)] = (uint16_t)(ip - 1);
+      uint32_t h = hash14(d, mask);
+      cand = table[h];
+      table[h] = (uint16_t)ip;
+      if (in_ld4(v, cand) != d) break;
+    }
+  }
+}
+
+struct CompressTArgs {
+  const uint8_t* in_base;   // contiguous stream, block i = bytes [65536 i, ...)
+  uint8_t* out_base;        // scratch slots
+  uint16_t* tables;         // count x 16384 entries, zeroed
+  uint64_t total_len;
+  uint64_t out_stride;
+  const uint32_t* crc;
+  uint32_t* out_len;
+  uint32_t count;
+  uint32_t mode;            // kModeFrame or kModeRawBlock
+};
+// Frames: stored chunks only get their 8-byte header here; compact_kernel takes the payload
+// straight from the input (slot[0] == 0x01 marks them).
+__global__ void __launch_bounds__(64) compress_thread_kernel(CompressTArgs a) {
+  uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
+  if (job >= a.count) return;
+  uint64_t ioff = (uint64_t)job * kMaxBlock;
+  uint32_t len = (uint32_t)((a.total_len - ioff) < kMaxBlock ? (a.total_len - ioff) : kMaxBlock);
+  const uint8_t* in = a.in_base + ioff;
+  uint8_t* out = a.out_base + (uint64_t)job * a.out_stride;
+  uint16_t* table = a.tables + (size_t)job * kMaxTableEntries;
+  uint32_t total;
+  if (a.mode == kModeFrame) {
+    uint32_t crc = a.crc[job];
+    uint32_t hl = varint32_len(len), thr = len - len / 8, bl = kAborted, fl;
+    if (len >= kMinNonLiteral) bl = compress_block_thread(in, len, out + 8 + hl, table, thr);
+    if (bl != kAborted && bl <= thr) {
+      uint32_t x = len, i = 0;
+      while (x >= 0x80) { out[8 + i++] = (uint8_t)(x | 0x80); x >>= 7; }
+      out[8 + i] = (uint8_t)x;
+      fl = hl + bl + 4;
+      out[0] = 0x00;
+    } else {
+      fl = len + 4;
+      out[0] = 0x01;
+    }
+    out[1] = (uint8_t)fl; out[2] = (uint8_t)(fl >> 8); out[3] = (uint8_t)(fl >> 16);
+    out[4] = (uint8_t)crc; out[5] = (uint8_t)(crc >> 8); out[6] = (uint8_t)(crc >> 16); out[7] = (uint8_t)(crc >> 24);
+    total = fl + 4;
+  } else {
+    total = compress_block_thread(in, len, out, table, kNoAbort);
+  }
+  a.out_len[job] = total;
 }
 
 // ===================================================================== CRC kernels
@@ -800,22 +953,33 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* lens, uint64
   if (threadIdx.x == 0) *total = carry_s;
 }
 
+// Cooperative CTA copy, any alignment: dst-aligned 32-bit stores, funnel-shifted loads.
+__device__ __forceinline__ void block_copy(uint8_t* d, const uint8_t* s, uint32_t n) {
+  uint32_t head = umin32(n, (uint32_t)((0 - (uintptr_t)d) & 3));
+  if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
+  uint32_t words = (n - head) >> 2;
+  uint32_t* dw = (uint32_t*)(d + head);
+  const uint8_t* sp = s + head;
+  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dw[i] = load32u(sp + 4 * i);
+  uint32_t done = head + 4 * words;
+  if (threadIdx.x < n - done) d[done + threadIdx.x] = s[done + threadIdx.x];
+}
 // Gather variable-length job outputs (slot i at i*stride, lens[i] bytes) to dst + offs[i].
-// One CTA per job (grid-stride), dst-aligned 32-bit stores.
+// One CTA per job (grid-stride).  With `in_base` set (framed mode), a stored chunk (slot[0] == 0x01)
+// only has its 8-byte header in the slot; its payload is block i of the input.
 __global__ void __launch_bounds__(256) compact_kernel(const uint8_t* scratch, uint64_t stride, const uint32_t* lens,
-                                                      const uint64_t* offs, uint8_t* dst, uint32_t count) {
+                                                      const uint64_t* offs, uint8_t* dst, uint32_t count,
+                                                      const uint8_t* in_base) {
   for (uint32_t job = blockIdx.x; job < count; job += gridDim.x) {
     const uint8_t* s = scratch + (uint64_t)job * stride;
     uint8_t* d = dst + offs[job];
     uint32_t n = lens[job];
-    uint32_t head = umin32(n, (uint32_t)((0 - (uintptr_t)d) & 3));
-    if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
-    uint32_t words = (n - head) >> 2;
-    uint32_t* dw = (uint32_t*)(d + head);
-    const uint8_t* sp = s + head;
-    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dw[i] = load32u(sp + 4 * i);
-    uint32_t done = head + 4 * words;
-    if (threadIdx.x < n - done) d[done + threadIdx.x] = s[done + threadIdx.x];
+    if (in_base != nullptr && s[0] == 0x01) {
+      if (threadIdx.x < 8) d[threadIdx.x] = s[threadIdx.x];
+      block_copy(d + 8, in_base + (uint64_t)job * kMaxBlock, n - 8);
+    } else {
+      block_copy(d, s, n);
+    }
   }
 }
 

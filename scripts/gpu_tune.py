@@ -28,7 +28,7 @@ dc = DeviceCodec(lib)
 d_in = torch.from_numpy(data).cuda()
 d_expect = torch.from_numpy(stream).cuda()
 out = torch.empty(int(lib.snb_max_compressed_len_framed(n)), dtype=torch.uint8, device="cuda")
-variants = [(a, w) for a in (1, 2) for w in (5, 6, 7)]
+variants = [(3, 0), (2, 7), (1, 7)]
 if len(sys.argv) > 3:
     variants = [tuple(int(x) for x in v.split(":")) for v in sys.argv[3].split(",")]
 dc.set_profiling(True)

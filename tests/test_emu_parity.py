@@ -80,3 +80,21 @@ def test_decoder_differential_fuzz(emu_api, oracle):
     fbase = oracle.encode_framed(read_data("html")[:2000] + bytes(rng.integers(0, 256, 300, dtype=np.uint8)))
     for s in P.mutate_streams(oracle, fbase, rng, 40):
         P.check_framed_decode_parity(emu_api, oracle, s, 4096)
+
+
+@pytest.mark.parametrize("algo", [1, 2, 3])
+def test_every_block_encoder_variant(emu_api, oracle, algo):
+    """The three block encoders (per-step warp, window-resolve warp, thread-per-block with the table in
+    global memory) are byte-identical; the auto mode picks between the last two by batch size."""
+    lib = emu_api.lib
+    lib.snb_set_compress_algo(algo)
+    try:
+        for name, cut in [("alice29.txt", 70000), ("paper-100k.pdf", 102400), ("kppkn.gtb", 20000)]:
+            d = read_data(name)[:cut]
+            P.check_raw(emu_api, oracle, d)
+            P.check_framed(emu_api, oracle, d)
+        for n in [0, 1, 16, 17, 18, 300, 65535, 65536, 65537]:
+            P.check_framed(emu_api, oracle, bytes(i & 0xFF for i in range(n)))
+            P.check_raw(emu_api, oracle, bytes(n))
+    finally:
+        lib.snb_set_compress_algo(0)
