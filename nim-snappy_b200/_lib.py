@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsnb200.so")
+LIB_PATH = os.environ.get("SNB_LIB") or os.path.join(HERE, "libsnb200.so")  # SNB_LIB: A/B builds of the same CUDA library (tuning only)
 
 OK, BUFFER_TOO_SMALL, INVALID_INPUT, CRC_MISMATCH, UNKNOWN_CHUNK = 0, 1, 2, 3, 4
 CUDA_ERROR, UNSUPPORTED = 100, 101

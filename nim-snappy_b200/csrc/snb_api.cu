@@ -84,9 +84,10 @@ struct Ctx {
   float prof[6] = {0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
   uint32_t call_launches = 0;
-  int compress_warps = 7;
-  int compress_algo = 0;  // 0 auto (thread-per-block for big batches, else window-resolve warps), 1/2 warp v1/v2, 3 thread
-  int thread_min_chunks = 4096;  // batches at least this large use one thread per block (tables in HBM)
+  int compress_warps = 7;    // 64 KiB blocks: encoder warps per SM with the table in shared memory
+  int compress_gwarps = 14;  // ... and with the table in global memory (L2)
+  int compress_algo = 0;  // 0 auto, 1/2/4 warp encoders v1/v2/v3, 3 one thread per block
+  int thread_min_chunks = 1 << 30;  // auto mode: batches at least this large use one thread per block (tables in HBM)
   std::string err;
 };
 Ctx g;
@@ -229,7 +230,7 @@ void prof_collect(int first_pair, int n_pairs, int slot0) {
 }
 
 // ---------------------------------------------------------------- launch geometry
-struct CompressGeom { uint32_t entries, warps, grid; size_t smem; };
+struct CompressGeom { uint32_t entries, warps, smem_warps, grid; size_t smem; };
 CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
   CompressGeom cg;
   uint32_t e = 256;
@@ -238,13 +239,16 @@ CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
   size_t tbytes = (size_t)e * 2;
   uint32_t ctas_per_sm;
   if (e == snb::kMaxTableEntries) {
-    cg.warps = (uint32_t)std::max(1, std::min(7, g.compress_warps));
+    // 7 x 32 KiB tables fill the shared memory of an SM; further warps keep their table in L2
+    cg.smem_warps = (uint32_t)std::max(0, std::min(7, g.compress_warps));
+    uint32_t extra = (uint32_t)std::max(0, std::min((int)(snb::kCompressMaxThreads / 32 - cg.smem_warps), g.compress_gwarps));
+    cg.warps = std::max(1u, cg.smem_warps + extra);
     ctas_per_sm = 1;
   } else {
-    cg.warps = 8;
+    cg.warps = cg.smem_warps = 8;
     ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (cg.warps * tbytes + 1024)));
   }
-  cg.smem = cg.warps * tbytes;
+  cg.smem = cg.smem_warps * tbytes;
   uint32_t need = (count + cg.warps - 1) / cg.warps;
   cg.grid = std::max(1u, std::min(need, (uint32_t)g.sms * ctas_per_sm));
   return cg;
@@ -289,7 +293,7 @@ int dev_compress_contig(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
       CKS(launch_crc(sin, nullptr, nullptr, slen, cnt, g.crcs.as<uint32_t>(), 1, st));
       if (p) prof_mark(1, st);
     }
-    if (g.compress_algo != 1 && g.compress_algo != 2 && cnt >= (uint32_t)g.thread_min_chunks || g.compress_algo == 3) {
+    if (g.compress_algo == 3 || (g.compress_algo == 0 && cnt >= (uint32_t)g.thread_min_chunks)) {
       // one thread per block, hash tables in global memory
       CK(g.tables.ensure((size_t)cnt * snb::kMaxTableEntries * 2));
       CK(cudaMemsetAsync(g.tables.p, 0, (size_t)cnt * snb::kMaxTableEntries * 2, st));
@@ -307,7 +311,10 @@ int dev_compress_contig(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
       CKS(next_counter(st, &a.counter));
       CompressGeom cg = compress_geom((uint32_t)kChunk, cnt);
       a.table_entries = cg.entries;
-      a.algo = (uint32_t)g.compress_algo;
+      a.smem_warps = cg.smem_warps;
+      CK(g.tables.ensure((size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2 + 256));
+      a.gtables = g.tables.as<uint16_t>();
+      a.algo = (uint32_t)((g.compress_algo == 1 || g.compress_algo == 2) ? g.compress_algo : 4);
       a.defer_stored = mode == snb::kModeFrame ? 1u : 0u;
       if (p) prof_mark(2, st);
       SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
@@ -817,7 +824,10 @@ int snb_dev_compress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const 
   CKS(next_counter(st, &a.counter));
   CompressGeom cg = compress_geom(max_len, (uint32_t)count);
   a.table_entries = cg.entries;
-  a.algo = (uint32_t)(g.compress_algo == 1 ? 1 : 2);
+  a.smem_warps = cg.smem_warps;
+  CK(g.tables.ensure((size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2 + 256));
+  a.gtables = g.tables.as<uint16_t>();
+  a.algo = (uint32_t)((g.compress_algo == 1 || g.compress_algo == 2) ? g.compress_algo : 4);
   a.defer_stored = 0;
   prof_mark(2, st);
   SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
@@ -883,7 +893,7 @@ int snb_get_profile(float* ms, int n) {
   return k;
 }
 uint64_t snb_kernel_launches(void) { return g.launches; }
-void snb_set_compress_warps(int warps) { g.compress_warps = warps; }
+void snb_set_compress_warps(int warps) { g.compress_warps = warps % 100; if (warps >= 100) g.compress_gwarps = warps / 100 - 1; }
 void snb_set_compress_algo(int algo) { g.compress_algo = algo; }
 void snb_set_thread_min_chunks(int n) { g.thread_min_chunks = n; }
 

@@ -40,6 +40,8 @@ enum : uint32_t { kKindCompressed = 0, kKindStored = 1, kKindVerifyOnly = 2 };
 __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
+// index of the lowest non-zero byte of x (x != 0)
+__device__ __forceinline__ uint32_t first_diff_byte(uint32_t x) { return (uint32_t)(__ffs((int)x) - 1) >> 3; }
 // Unaligned little-endian 32-bit load built from aligned words.  Only words holding at least
 // one requested byte are touched.
 __device__ __forceinline__ uint32_t load32u(const uint8_t* p) {
@@ -654,6 +656,300 @@ __device__ __forceinline__ uint32_t compress_block_v2(const uint8_t* __restrict_
 #undef SNB_FINISH
 }
 
+// --------------------------------------------------------------------- encodeBlock, v3
+// Window-parallel parse.  Same byte-exact result as v1/v2, but the walk through a 32-position
+// window is itself data parallel:
+//
+//   fetch    lane l owns position b+l (b a multiple of 32): 12 own bytes, hash, table entry T,
+//            12 candidate bytes.  Issued one window ahead; T is re-read after the previous
+//            window's commit and the candidate reloaded only if the entry changed.
+//   resolve  match length ml (0..12) against T, copy tag, match.any group of the hash.
+//   parse    as a *chain arrival* (post-copy lookup, encoder.nim:364-380) every lane knows its
+//            event: the copy at itself (hit) or the literal up to the first hit lane after it,
+//            then the copy there; and so the next chain arrival J.  Pointer doubling over J
+//            (3 rounds: arrivals are >= 4 apart) marks the arrivals actually on the path and sums
+//            their output sizes, which gives every node its output offset.
+//   verify   the inserts implied by the path are exact unless a looked-up lane has an earlier lane
+//            of its hash group inserted in this window (its true candidate is then that lane), or
+//            a match reaches the 12-byte horizon.  The path is accepted up to the first such node;
+//            that node is redone by a serial step straight on the table (v1 style).
+//   commit   last inserted lane of each hash group writes the table.
+//
+// Chunk tails, strided literal runs (>= 32 probes) and the rare conflicts take the serial step.
+struct WinData {
+  uint32_t a0, a1, a2;  // in[p .. p+12)
+  uint32_t h, T;        // hash of a0, table entry as of the fetch
+  uint32_t c0, c1, c2;  // in[T .. T+12)
+};
+// 12 bytes at p, p + 12 <= len (no clamping needed: every touched word holds an input byte)
+__device__ __forceinline__ void in_ld12u(const InView& v, uint32_t p, uint32_t& b0, uint32_t& b1, uint32_t& b2) {
+  uint32_t i = p + v.mis, k = i >> 2, s = (i & 3) * 8;
+  uint32_t w0 = __ldg(v.w + k), w1 = __ldg(v.w + k + 1), w2 = __ldg(v.w + k + 2), w3 = __ldg(v.w + umin32(k + 3, v.last));
+  b0 = __funnelshift_r(w0, w1, s); b1 = __funnelshift_r(w1, w2, s); b2 = __funnelshift_r(w2, w3, s);
+}
+__device__ __forceinline__ void win_fetch(const InView& v, const uint16_t* table, uint32_t mask, uint32_t p, WinData& w) {
+  in_ld12u(v, p, w.a0, w.a1, w.a2);
+  w.h = hash14(w.a0, mask);
+  w.T = table[w.h];
+  in_ld12u(v, w.T, w.c0, w.c1, w.c2);
+}
+
+__device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict__ in, uint32_t len,
+                                                      uint8_t* __restrict__ out, uint16_t* table,
+                                                      uint32_t abort_thr, uint32_t lane) {
+  InView v;
+  v.mis = (uint32_t)((uintptr_t)in & 3);
+  v.w = (const uint32_t*)(in - v.mis);
+  v.last = (len + v.mis - 1) >> 2;
+  if (len < kMinNonLiteral) return emit_literal_v2(out, v, 0, len, lane);
+
+  uint32_t tsize = 256;
+  while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
+  const uint32_t mask = tsize - 1;
+  {
+    uint32_t* t32 = (uint32_t*)table;
+    for (uint32_t i = lane; i < tsize / 2; i += 32) t32[i] = 0;
+  }
+  const uint32_t ip_limit = len - kInputMargin;
+  const uint32_t below = (1u << lane) - 1u;          // lanes before mine
+  const uint32_t above = ~((2u << lane) - 1u);       // lanes after mine
+  uint32_t op = 0;
+  uint32_t ip = 0;          // chain mode: position of the pending post-copy lookup (<= ip_limit)
+  uint32_t next_emit = 0;   // literal mode: start of the pending literal
+  uint32_t pp = 1;          // literal mode: next probe position
+  uint32_t k = 0;           // literal mode: probes already done in this run
+  bool chain = false, force_slow = false;
+  bool m1_done = false;     // chain mode, ip on a window boundary: ip-1 has already been inserted
+  WinData cur, nxt;
+  uint32_t cur_b = 0xffffffffu, nxt_b = 0xffffffffu;
+
+#define SNB_FINISH(from)                                                          \
+  do {                                                                            \
+    uint32_t f_ = (from);                                                         \
+    if (f_ < len) {                                                               \
+      uint32_t n_ = len - f_;                                                     \
+      if (op + literal_size(n_) > abort_thr) return kAborted;                     \
+      op += emit_literal_v2(out + op, v, f_, n_, lane);                           \
+    }                                                                             \
+    return op;                                                                    \
+  } while (0)
+
+  for (;;) {
+    __syncwarp();  // table writes (zeroing / previous commit / serial step) visible to every lane
+    const uint32_t b = (chain ? ip : pp) & ~31u;
+
+    if (force_slow || b + 32 >= ip_limit || (!chain && k >= 32)) {
+      force_slow = false;
+      m1_done = false;
+      if (chain) {
+        // ---- one serial chain step straight on the table (encoder.nim:364-380)
+        const uint32_t d1 = in_ld4(v, ip - 1), d = in_ld4(v, ip);
+        const uint32_t h1 = hash14(d1, mask), hh = hash14(d, mask);
+        const uint32_t tv = table[hh];
+        const uint32_t cand = (hh == h1) ? ip - 1 : tv;
+        __syncwarp();  // every lane has read before lane 0 writes
+        if (lane == 0) { table[h1] = (uint16_t)(ip - 1); table[hh] = (uint16_t)ip; }
+        const uint32_t m = common_prefix_v2(v, len, cand, ip, lane);
+        if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }   // :379-380
+        op += emit_copy_v2(out + op, ip - cand, m, lane);
+        ip += m;
+        if (op > abort_thr) return kAborted;
+        if (ip > ip_limit) SNB_FINISH(ip);
+        continue;
+      }
+      // ---- serial literal scan from (pp, k): 32 strided probes per step (encoder.nim:281-331)
+      uint32_t wip = pp, wskip = 32 + k;
+      uint32_t hit_ip = 0, hit_cand = 0;
+      bool found = false;
+      for (;;) {
+        uint32_t pos = wip, sk = wskip;
+        for (uint32_t j = 0; j < lane; j++) { uint32_t st = sk >> 5; sk += st; pos += st; }
+        uint32_t step = sk >> 5, sk_after = sk + step;
+        bool valid = (pos <= ip_limit) && (pos + step <= ip_limit);
+        uint32_t d = 0, h = 0x10000u + lane, tv = 0;
+        if (valid) { d = in_ld4(v, pos); h = hash14(d, mask); tv = table[h]; }
+        uint32_t grp = __match_any_sync(kFull, h);
+        uint32_t earlier = grp & below;
+        int src = earlier ? 31 - __clz((int)earlier) : (int)lane;
+        uint32_t pe = __shfl_sync(kFull, pos, src);
+        uint32_t c = earlier ? pe : tv;
+        bool hit = valid && (in_ld4(v, c) == d);
+        uint32_t hitmask = __ballot_sync(kFull, hit);
+        uint32_t vmask = __ballot_sync(kFull, valid);
+        if (hitmask) {
+          int kh = __ffs((int)hitmask) - 1;
+          uint32_t commit = (2u << kh) - 1u;
+          if (((commit >> lane) & 1u) && ((grp & commit) >> lane) == 1u) table[h] = (uint16_t)pos;
+          hit_ip = __shfl_sync(kFull, pos, kh);
+          hit_cand = __shfl_sync(kFull, c, kh);
+          found = true;
+          break;
+        }
+        if (vmask != kFull) break;
+        if ((grp >> lane) == 1u) table[h] = (uint16_t)pos;
+        wip = __shfl_sync(kFull, pos + step, 31);
+        wskip = __shfl_sync(kFull, sk_after, 31);
+        __syncwarp();
+      }
+      if (!found) SNB_FINISH(next_emit);
+      {
+        uint32_t n = hit_ip - next_emit;
+        if (op + literal_size(n) > abort_thr) return kAborted;
+        op += emit_literal_v2(out + op, v, next_emit, n, lane);
+      }
+      uint32_t m = 4 + common_prefix_v2(v, len, hit_cand + 4, hit_ip + 4, lane);
+      op += emit_copy_v2(out + op, hit_ip - hit_cand, m, lane);
+      ip = hit_ip + m;
+      if (op > abort_thr) return kAborted;
+      if (ip > ip_limit) SNB_FINISH(ip);
+      chain = true;
+      continue;
+    }
+
+    // ---- window data for [b, b+32): every lane is a valid lookup position (b + 32 < ip_limit)
+    const uint32_t p = b + lane;
+    if (chain && ip == b && !m1_done) {  // arrival on the window boundary after a serial step: ip-1 is not a lane here
+      const uint32_t d1 = in_ld4(v, ip - 1);
+      if (lane == 0) table[hash14(d1, mask)] = (uint16_t)(ip - 1);
+      __syncwarp();
+    }
+    m1_done = false;
+    if (cur_b != b) {
+      if (nxt_b == b) cur = nxt; else win_fetch(v, table, mask, p, cur);
+      cur_b = b;
+    }
+    {  // re-validate against the committed table
+      const uint32_t T = table[cur.h];
+      if (T != cur.T) { cur.T = T; in_ld12u(v, T, cur.c0, cur.c1, cur.c2); }
+    }
+    if (nxt_b != b + 32 && b + 64 < ip_limit) { win_fetch(v, table, mask, p + 32, nxt); nxt_b = b + 32; }
+
+    // ---- resolve
+    const uint32_t x0 = cur.a0 ^ cur.c0, x1 = cur.a1 ^ cur.c1, x2 = cur.a2 ^ cur.c2;
+    const uint32_t ml = x0 ? first_diff_byte(x0) : (x1 ? 4 + first_diff_byte(x1) : (x2 ? 8 + first_diff_byte(x2) : 12));
+    const uint32_t off = p - cur.T;
+    const bool c2 = off >= 2048;   // ml <= 11 whenever the tag is used (encoder.nim:113-125)
+    const uint32_t tb = c2 ? ((((ml - 1) << 2) | 2u) | (off << 8))
+                           : ((((off >> 8) << 5) | ((ml - 4) << 2) | 1u) | ((off & 0xff) << 8));
+    const uint32_t rec = (tb & 0xffffffu) | (c2 ? 1u << 24 : 0u) | (ml << 25);
+    const uint32_t grp = __match_any_sync(kFull, cur.h);
+    const uint32_t eg = grp & below;                   // earlier lanes of my hash group
+    const bool hit = ml >= 4;
+    const uint32_t HB = __ballot_sync(kFull, hit);
+
+    uint32_t ins = 0;   // lanes inserted (accepted) in this pass
+    uint32_t c0;        // first chain-arrival lane of this pass (>= 32: outside the window)
+    if (!chain) {
+      // ---- the literal run entering the window: stride-1 probes at lanes [l0, bend)
+      const uint32_t l0 = pp - b;
+      const uint32_t bend = umin32(32u, l0 + (32u - k));
+      const uint32_t range = (0xffffffffu << l0) & (bend >= 32 ? 0xffffffffu : ((1u << bend) - 1u));
+      const uint32_t qh = HB & range;
+      const uint32_t q0 = qh ? (uint32_t)__ffs((int)qh) - 1u : 32u;
+      const uint32_t run = range & ((2u << (q0 & 31)) - 1u | (q0 >= 32 ? 0xffffffffu : 0u));   // probes performed
+      const uint32_t stale = __ballot_sync(kFull, (eg & run) != 0) & run;
+      const uint32_t q0rec = __shfl_sync(kFull, rec, (int)(q0 & 31));
+      const uint32_t q0ml = q0rec >> 25;
+      if (stale || (q0 < 32 && q0ml >= 12)) { force_slow = true; continue; }
+      if (q0 >= 32) {  // every probe missed: insert them and move on (k == 32 switches to the strided scan)
+        if (((run >> lane) & 1u) && ((grp & run) >> lane) == 1u) table[cur.h] = (uint16_t)p;
+        k += (uint32_t)__popc(run);
+        pp = b + bend;
+        continue;
+      }
+      {  // :336-338, then the copy at q0
+        const uint32_t n = b + q0 - next_emit;
+        if (op + literal_size(n) > abort_thr) return kAborted;
+        op += emit_literal_v2(out + op, v, next_emit, n, lane);
+        if (lane == 0) {
+          uint8_t* o = out + op;
+          o[0] = (uint8_t)q0rec; o[1] = (uint8_t)(q0rec >> 8);
+          if ((q0rec >> 24) & 1u) o[2] = (uint8_t)(q0rec >> 16);
+        }
+        op += ((q0rec >> 24) & 1u) ? 3u : 2u;
+      }
+      ins = run;
+      chain = true;
+      c0 = q0 + q0ml;
+      ip = b + c0;
+    } else {
+      c0 = ip - b;
+    }
+
+    bool pend_insert = false;
+    if (c0 < 32) {
+      // ---- every lane as a chain arrival: its event lane, the next arrival, its output size
+      const uint32_t qb = hit ? (1u << lane) : (HB & above);
+      const uint32_t evt = qb ? (uint32_t)__ffs((int)qb) - 1u : 32u;
+      const uint32_t erec = __shfl_sync(kFull, rec, (int)(evt & 31));
+      const uint32_t eml = erec >> 25;
+      const uint32_t J0 = evt < 32 ? evt + eml : 64u;   // >= 32 leaves the window, 64: in literal mode
+      const uint32_t litn = evt - lane;
+      const uint32_t sz = evt < 32 ? (hit ? 0u : litn + 1u) + (((erec >> 24) & 1u) ? 3u : 2u) : 0u;
+      uint32_t J = J0, D = sz, R = 1u << c0;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const uint32_t contrib = (((R >> lane) & 1u) && J < 32) ? (1u << J) : 0u;
+        R |= __reduce_or_sync(kFull, contrib);
+        const uint32_t jn = __shfl_sync(kFull, J, (int)(J & 31));
+        const uint32_t dn = __shfl_sync(kFull, D, (int)(J & 31));
+        if (J < 32) { D += dn; J = jn; }
+      }
+      const bool onp = (R >> lane) & 1u;
+      // inserts of a node: ip-1, ip, then the probes up to its event (encoder.nim:371-377, :293-294)
+      const uint32_t nmask = (0xffffffffu << (lane ? lane - 1 : 0)) & ((2u << (evt < 32 ? evt : 31u)) - 1u);
+      const uint32_t ins_all = ins | __reduce_or_sync(kFull, onp ? nmask : 0u);
+      const uint32_t stale = __ballot_sync(kFull, (eg & ins_all) != 0) & ins_all;
+      const bool mybad = onp && (((stale & nmask) != 0) || (evt < 32 && eml >= 12));
+      const uint32_t BAD = __ballot_sync(kFull, mybad);
+      const uint32_t cb = BAD ? (uint32_t)__ffs((int)BAD) - 1u : 32u;
+      const uint32_t ACC = R & (cb >= 32 ? 0xffffffffu : ((1u << cb) - 1u));
+      const bool acc = (ACC >> lane) & 1u;
+      ins = BAD ? (ins | __reduce_or_sync(kFull, acc ? nmask : 0u)) : ins_all;
+      const uint32_t Dc0 = __shfl_sync(kFull, D, (int)c0);
+      const uint32_t Dcb = __shfl_sync(kFull, D, (int)(cb & 31));
+      const uint32_t off_me = op + (Dc0 - D);           // output offset of my node (accepted lanes)
+      if (acc && evt < 32) {
+        uint8_t* o = out + off_me;
+        if (!hit) { o[0] = (uint8_t)((litn - 1) << 2); o += 1 + litn; }
+        o[0] = (uint8_t)erec; o[1] = (uint8_t)(erec >> 8);
+        if ((erec >> 24) & 1u) o[2] = (uint8_t)(erec >> 16);
+      }
+      {  // literal bytes: lanes from a missed accepted node up to its event write their own byte
+        const uint32_t nm = ACC & ((2u << lane) - 1u);
+        const uint32_t node = nm ? 31u - (uint32_t)__clz((int)nm) : 0u;
+        const uint32_t pk = __shfl_sync(kFull, off_me | (evt << 20) | (hit ? 1u << 26 : 0u), (int)node);
+        const uint32_t ev = (pk >> 20) & 63u;
+        if (nm && !((pk >> 26) & 1u) && ev < 32 && lane < ev) out[(pk & 0xfffffu) + 1 + (lane - node)] = (uint8_t)cur.a0;
+      }
+      op += Dc0 - (BAD ? Dcb : 0u);
+      if (BAD) {
+        ip = b + cb; force_slow = true;
+      } else {
+        const uint32_t cl = 31u - (uint32_t)__clz((int)R);
+        const uint32_t Jl = __shfl_sync(kFull, J0, (int)cl);
+        if (Jl == 64u) { chain = false; next_emit = b + cl; pp = b + 32; k = 31 - cl; }
+        else ip = b + Jl;
+      }
+    }
+    // the next arrival's ip-1 insert when no window pass will own it (lane c-1 of the node rule)
+    if (chain && !force_slow && (ip & 31u) == 0 && ip <= ip_limit) {
+      if (ip == b + 32) ins |= 1u << 31; else pend_insert = true;
+      m1_done = true;
+    }
+    // ---- commit: the last inserted lane of each hash group writes the table
+    if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[cur.h] = (uint16_t)p;
+    if (op > abort_thr) return kAborted;
+    if (chain && ip > ip_limit) SNB_FINISH(ip);
+    if (pend_insert) {
+      __syncwarp();
+      const uint32_t d1 = in_ld4(v, ip - 1);
+      if (lane == 0) table[hash14(d1, mask)] = (uint16_t)(ip - 1);
+    }
+  }
+#undef SNB_FINISH
+}
+
 struct CompressArgs {
   const uint8_t* in_base;
   uint8_t* out_base;
@@ -668,8 +964,10 @@ struct CompressArgs {
   uint32_t count;
   uint32_t mode;
   uint32_t table_entries;   // per-warp shared-memory table capacity (u16 entries)
-  uint32_t algo;            // 1: compress_block_warp (v1), otherwise compress_block_v2
+  uint32_t algo;            // 1: compress_block_warp (v1), 2: compress_block_v2, otherwise compress_block_v3
   uint32_t defer_stored;    // 1: stored frames get only their header here (compact_kernel copies the payload)
+  uint16_t* gtables;        // hash tables of the warps beyond smem_warps (table_entries each)
+  uint32_t smem_warps;      // warps per CTA whose table lives in shared memory
 };
 
 __device__ __forceinline__ uint32_t put_varint32(uint8_t* o, uint32_t v, uint32_t lane) {
@@ -685,7 +983,8 @@ __device__ __forceinline__ uint32_t varint32_len(uint32_t v) {
 __device__ __forceinline__ uint32_t encode_block(uint32_t algo, const uint8_t* in, uint32_t len, uint8_t* out,
                                                  uint16_t* table, uint32_t abort_thr, uint32_t lane) {
   if (algo == 1) return compress_block_warp(in, len, out, table, abort_thr, lane);
-  return compress_block_v2(in, len, out, table, abort_thr, lane);
+  if (algo == 2) return compress_block_v2(in, len, out, table, abort_thr, lane);
+  return compress_block_v3(in, len, out, table, abort_thr, lane);
 }
 
 // One job = one encodeFrame (encoder.nim:385-426), one bare encodeBlock, or one whole
@@ -696,13 +995,16 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
   uint64_t ooff = a.out_off ? a.out_off[job] : (uint64_t)job * a.out_stride;
   const uint8_t* in = a.in_base + ioff;
   uint8_t* out = a.out_base + ooff;
+  // where the block goes inside the job's output, and whether a block is encoded at all
+  const bool frame = a.mode == kModeFrame;
+  const uint32_t hl = a.mode == kModeRawBlock ? 0u : varint32_len(len);
+  const uint32_t pre = frame ? 8u + hl : hl;
+  const uint32_t thr = frame ? len - len / 8 : kNoAbort;
+  uint32_t bl = frame ? kAborted : 0u;
+  if (frame ? len >= kMinNonLiteral : len > 0) bl = encode_block(a.algo, in, len, out + pre, table, thr, lane);  // encoder.nim:401-406
   uint32_t total;
-  if (a.mode == kModeFrame) {
+  if (frame) {
     uint32_t crc = a.crc[job];
-    uint32_t hl = varint32_len(len);
-    uint32_t thr = len - len / 8;
-    uint32_t bl = kAborted;
-    if (len >= kMinNonLiteral) bl = encode_block(a.algo, in, len, out + 8 + hl, table, thr, lane);  // :401-406
     uint32_t fl;
     if (bl != kAborted && bl <= thr) {  // :408-416
       put_varint32(out + 8, len, lane);
@@ -718,21 +1020,28 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
       out[4] = (uint8_t)crc; out[5] = (uint8_t)(crc >> 8); out[6] = (uint8_t)(crc >> 16); out[7] = (uint8_t)(crc >> 24);
     }
     total = fl + 4;
-  } else if (a.mode == kModeRawBlock) {
-    total = len ? encode_block(a.algo, in, len, out, table, kNoAbort, lane) : 0;
   } else {
-    uint32_t hl = put_varint32(out, len, lane);
-    total = hl + (len ? encode_block(a.algo, in, len, out + hl, table, kNoAbort, lane) : 0);
+    if (a.mode == kModeRawMessage) put_varint32(out, len, lane);  // snappy.nim:49-50
+    total = hl + bl;
   }
   if (lane == 0) a.out_len[job] = total;
 }
 
-// Persistent kernel: blockDim.x/32 warps per CTA, each with its own hash table in dynamic
-// shared memory, pulling jobs from a global counter.
-__global__ void __launch_bounds__(256) compress_kernel(CompressArgs a) {
+// Persistent kernel: blockDim.x/32 warps per CTA pulling jobs from a global counter.  The first
+// `smem_warps` warps keep their hash table in dynamic shared memory; the others use a 32 KiB
+// slice of `gtables` (global memory, L2 resident: 148 x a few x 32 KiB) -- same code, the table
+// pointer is generic.  The extra warps are what fills the issue slots: one encoder warp is a
+// single dependent chain.
+#ifndef SNB_COMPRESS_MAXT
+#define SNB_COMPRESS_MAXT 768
+#endif
+constexpr uint32_t kCompressMaxThreads = SNB_COMPRESS_MAXT;  // register budget: 65536 / 768 = 85 per thread
+__global__ void __launch_bounds__(kCompressMaxThreads, 1) compress_kernel(CompressArgs a) {
   SNB_DYN_SMEM(smem);
   uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint16_t* table = (uint16_t*)smem + (size_t)warp * a.table_entries;
+  uint16_t* table = warp < a.smem_warps
+                        ? (uint16_t*)smem + (size_t)warp * a.table_entries
+                        : a.gtables + ((size_t)blockIdx.x * (blockDim.x / 32 - a.smem_warps) + (warp - a.smem_warps)) * a.table_entries;
   for (;;) {
     uint32_t job = 0;
     if (lane == 0) job = atomicAdd(a.counter, 1u);
@@ -744,115 +1053,196 @@ __global__ void __launch_bounds__(256) compress_kernel(CompressArgs a) {
 }
 
 // --------------------------------------------------------------------- encodeBlock, one THREAD per block
-// For large batches the serial chain is better hidden by running every block at once: one
-// thread per 64 KiB block, hash table in global memory (32 KiB per thread, zeroed by the host),
-// the reference's loop verbatim (encoder.nim:184-383).  Tens of thousands of independent
-// dependent-load chains keep HBM busy; the warp-cooperative kernel above wins only when the
-// batch is too small to fill the machine this way.
-__device__ __forceinline__ uint32_t thread_emit_literal(uint8_t* o, const InView& v, uint32_t s, uint32_t n) {
-  uint32_t m = (n - 1) & 0xffff, w;
-  if (m < 60) { o[0] = (uint8_t)(m << 2); w = 1; }
-  else if (m < 256) { o[0] = 60 << 2; o[1] = (uint8_t)m; w = 2; }
-  else { o[0] = 61 << 2; o[1] = (uint8_t)m; o[2] = (uint8_t)(m >> 8); w = 3; }
-  const uint8_t* src = (const uint8_t*)v.w + v.mis + s;
-  for (uint32_t i = 0; i < n; i++) o[w + i] = __ldg(src + i);
-  return w + n;
+// For large batches the serial chain of the reference's loop (encoder.nim:184-383) is better
+// hidden by running every block at once: one thread per 64 KiB block, hash table in global
+// memory (32 KiB per thread, zeroed by the host).  The loop is restated as a LOCKSTEP state
+// machine so that the 32 blocks of a warp never serialise their memory latencies: every
+// iteration each lane performs exactly one of
+//   SCAN    one literal-scan probe            (encoder.nim:281-331)
+//   CHAIN   one post-copy insert + lookup     (encoder.nim:364-380)
+//   EXTEND  12 more bytes of findMatchLength  (encoder.nim:130-182)
+//   LIT     16 more bytes of a long literal   (encoder.nim:57-73)
+// with all parse-independent loads issued first, then the table access, then the candidate
+// bytes, then a divergent but memory-free state update.  Output goes through a per-thread
+// byte writer that only issues aligned 32-bit stores.
+enum : uint32_t { kTScan = 0, kTChain = 1, kTExtend = 2, kTLit = 3, kTDone = 4 };
+
+struct TWriter {
+  uint32_t* w;     // next aligned word of the output slot
+  uint32_t lo, hi; // pending bytes (low `fill` bytes of lo valid, hi = overflow of the last put)
+  uint32_t fill;   // 0..3 between puts
+};
+// append k (1..4) bytes held in the low bytes of v (no bits above 8k set)
+__device__ __forceinline__ void tw_put(TWriter& b, uint32_t v, uint32_t k) {
+  uint32_t sh = 8 * b.fill;
+  b.lo |= v << sh;
+  b.hi = __funnelshift_l(v, 0, sh);
+  b.fill += k;
+  if (b.fill >= 4) { *b.w++ = b.lo; b.lo = b.hi; b.fill -= 4; }
 }
-__device__ __forceinline__ uint32_t thread_emit_copy(uint8_t* o, uint32_t off, uint32_t len) {
-  uint32_t w = 0;
-  while (len >= 68) { o[w] = (63 << 2) | 2; o[w + 1] = (uint8_t)off; o[w + 2] = (uint8_t)(off >> 8); w += 3; len -= 64; }
-  if (len > 64) { o[w] = (59 << 2) | 2; o[w + 1] = (uint8_t)off; o[w + 2] = (uint8_t)(off >> 8); w += 3; len -= 60; }
-  if (len >= 12 || off >= 2048) {
-    o[w] = (uint8_t)(((len - 1) << 2) | 2); o[w + 1] = (uint8_t)off; o[w + 2] = (uint8_t)(off >> 8);
-    return w + 3;
+__device__ __forceinline__ void tw_flush(TWriter& b) {
+  uint8_t* p = (uint8_t*)b.w;
+  for (uint32_t i = 0; i < b.fill; i++) p[i] = (uint8_t)(b.lo >> (8 * i));
+}
+// k (0..16) bytes held in b0..b3
+__device__ __forceinline__ void tw_put16(TWriter& b, uint32_t k, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+  const uint32_t w[4] = {b0, b1, b2, b3};
+#pragma unroll
+  for (uint32_t j = 0; j < 4; j++) {
+    if (k > 4 * j) {
+      uint32_t kk = umin32(4, k - 4 * j);
+      tw_put(b, kk == 4 ? w[j] : (w[j] & ((1u << (8 * kk)) - 1u)), kk);
+    }
   }
-  o[w] = (uint8_t)(((off >> 8) << 5) | ((len - 4) << 2) | 1);
-  o[w + 1] = (uint8_t)off;
+}
+// literal tag of an n-byte literal (encoder.nim:57-73); returns its size
+__device__ __forceinline__ uint32_t tw_literal_tag(TWriter& b, uint32_t n) {
+  uint32_t m = (n - 1) & 0xffff;
+  if (m < 60) { tw_put(b, m << 2, 1); return 1; }
+  if (m < 256) { tw_put(b, (60u << 2) | (m << 8), 2); return 2; }
+  tw_put(b, (61u << 2) | (m << 8), 3);
+  return 3;
+}
+// encoder.nim:81-125; returns bytes appended
+__device__ __forceinline__ uint32_t tw_copy(TWriter& b, uint32_t off, uint32_t len) {
+  uint32_t w = 0;
+  while (len >= 68) { tw_put(b, ((63u << 2) | 2u) | (off << 8), 3); w += 3; len -= 64; }
+  if (len > 64) { tw_put(b, ((59u << 2) | 2u) | (off << 8), 3); w += 3; len -= 60; }
+  if (len >= 12 || off >= 2048) { tw_put(b, (((len - 1) << 2) | 2u) | (off << 8), 3); return w + 3; }
+  tw_put(b, (((off >> 8) << 5) | ((len - 4) << 2) | 1u) | ((off & 0xff) << 8), 2);
   return w + 2;
 }
-// longest common prefix of positions s1 < s2, s2 side bounded by len (encoder.nim:130-182)
-__device__ __forceinline__ uint32_t thread_match_len(const InView& v, uint32_t len, uint32_t s1, uint32_t s2) {
-  uint32_t m = 0;
-  while (s2 + m + 8 <= len) {
-    uint32_t a_lo, a_hi, b_lo, b_hi;
-    in_ld8(v, s1 + m, a_lo, a_hi);
-    in_ld8(v, s2 + m, b_lo, b_hi);
-    uint32_t x_lo = a_lo ^ b_lo, x_hi = a_hi ^ b_hi;
-    if (x_lo) return m + ((uint32_t)(__ffs((int)x_lo) - 1) >> 3);
-    if (x_hi) return m + 4 + ((uint32_t)(__ffs((int)x_hi) - 1) >> 3);
-    m += 8;
-  }
-  while (s2 + m < len && in_byte(v, s1 + m) == in_byte(v, s2 + m)) m++;
-  return m;
+// n (12 / 16) bytes at position p as little-endian words; words past the input end repeat the last one
+__device__ __forceinline__ void in_ld12(const InView& v, uint32_t p, uint32_t& b0, uint32_t& b1, uint32_t& b2) {
+  uint32_t i = p + v.mis, k = i >> 2, s = (i & 3) * 8;
+  uint32_t w0 = __ldg(v.w + umin32(k, v.last)), w1 = __ldg(v.w + umin32(k + 1, v.last));
+  uint32_t w2 = __ldg(v.w + umin32(k + 2, v.last)), w3 = __ldg(v.w + umin32(k + 3, v.last));
+  b0 = __funnelshift_r(w0, w1, s); b1 = __funnelshift_r(w1, w2, s); b2 = __funnelshift_r(w2, w3, s);
 }
-__device__ __forceinline__ uint32_t compress_block_thread(const uint8_t* __restrict__ in, uint32_t len,
-                                                          uint8_t* __restrict__ out, uint16_t* __restrict__ table,
-                                                          uint32_t abort_thr) {
+__device__ __forceinline__ void in_ld16(const InView& v, uint32_t p, uint32_t& b0, uint32_t& b1, uint32_t& b2,
+                                        uint32_t& b3) {
+  uint32_t i = p + v.mis, k = i >> 2, s = (i & 3) * 8;
+  uint32_t w0 = __ldg(v.w + umin32(k, v.last)), w1 = __ldg(v.w + umin32(k + 1, v.last));
+  uint32_t w2 = __ldg(v.w + umin32(k + 2, v.last)), w3 = __ldg(v.w + umin32(k + 3, v.last));
+  uint32_t w4 = __ldg(v.w + umin32(k + 4, v.last));
+  b0 = __funnelshift_r(w0, w1, s); b1 = __funnelshift_r(w1, w2, s);
+  b2 = __funnelshift_r(w2, w3, s); b3 = __funnelshift_r(w3, w4, s);
+}
+
+// Returns the encoded length (bytes appended to `wr`), or kAborted once the output would pass abort_thr.
+__device__ __forceinline__ uint32_t compress_block_thread(const uint8_t* __restrict__ in, uint32_t len, TWriter& wr,
+                                                          uint16_t* __restrict__ table, uint32_t abort_thr) {
   InView v;
   v.mis = (uint32_t)((uintptr_t)in & 3);
   v.w = (const uint32_t*)(in - v.mis);
   v.last = (len + v.mis - 1) >> 2;
-  if (len < kMinNonLiteral) return thread_emit_literal(out, v, 0, len);
+  if (len < kMinNonLiteral) {  // encoder.nim:227-229
+    uint32_t b0, b1, b2, b3;
+    in_ld16(v, 0, b0, b1, b2, b3);
+    uint32_t t = tw_literal_tag(wr, len);
+    tw_put16(wr, len, b0, b1, b2, b3);
+    return t + len;
+  }
   uint32_t tsize = 256;
   while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
   const uint32_t mask = tsize - 1;
   const uint32_t ip_limit = len - kInputMargin;
-  uint32_t ip = 0, op = 0;
-  for (;;) {
-    uint32_t next_emit = ip++;
-    uint32_t skip = 32, cand = 0;
-    bool found = false;
-    // encoder.nim:281-331; the 16 unrolled probes and the scan loop are the same per-probe step once
-    // "a probe happens only if ip + (skip >> 5) <= ip_limit" is applied uniformly (see compress_block_warp)
-    for (;;) {
-      uint32_t step = skip >> 5;
-      skip += step;
-      uint32_t next_ip = ip + step;
-      if (next_ip > ip_limit) break;
-      uint32_t d = in_ld4(v, ip), h = hash14(d, mask);
-      cand = table[h];
-      table[h] = (uint16_t)ip;
-      if (in_ld4(v, cand) == d) { found = true; break; }
-      ip = next_ip;
+
+  uint32_t mode = kTScan, op = 0;
+  uint32_t ip = 1, next_emit = 0, skip = 33, next_ip = 2;   // first probe of the first run (ip_limit >= 2)
+  uint32_t e_s1 = 0, e_s2 = 0, e_matched = 0, e_off = 0;    // EXTEND
+  uint32_t lit_src = 0, lit_n = 0;                          // LIT
+  uint32_t pend_cand = 0, pend_ml = 0;                      // LIT: the copy that follows (pend_ml == 0: block ends)
+  bool aborted = false;
+
+  // emitRemainder (encoder.nim:249-253 via :319-321 / :362-363)
+  auto finish_from = [&](uint32_t from) {
+    if (from >= len) { mode = kTDone; return; }
+    uint32_t n = len - from;
+    if (op + literal_size(n) > abort_thr) { aborted = true; mode = kTDone; return; }
+    op += tw_literal_tag(wr, n) + n;
+    lit_src = from; lit_n = n; pend_ml = 0; mode = kTLit;
+  };
+  // next probe of the current run: encoder.nim:311-321 (and the unrolled :281-309, same recurrence)
+  auto arm_scan = [&]() {
+    uint32_t step = skip >> 5;
+    skip += step;
+    next_ip = ip + step;
+    if (next_ip > ip_limit) finish_from(next_emit); else mode = kTScan;
+  };
+  // a copy of `matched` bytes at ip has been emitted (encoder.nim:358-363)
+  auto after_copy = [&](uint32_t matched) {
+    ip += matched;
+    if (op > abort_thr) { aborted = true; mode = kTDone; return; }
+    if (ip > ip_limit) finish_from(ip); else mode = kTChain;
+  };
+  // the match at ip against cand is known to be ml (4..8, 8 = at least 8) bytes long
+  auto begin_copy = [&](uint32_t cand, uint32_t ml) {
+    if (ml >= 8) {
+      e_s1 = cand + 8; e_s2 = ip + 8; e_matched = 8; e_off = ip - cand; mode = kTExtend;
+    } else {
+      op += tw_copy(wr, ip - cand, ml);
+      after_copy(ml);
     }
-    if (!found) {
-      uint32_t n = len - next_emit;
-      if (op + literal_size(n) > abort_thr) return kAborted;
-      return op + thread_emit_literal(out + op, v, next_emit, n);
-    }
-    {
-      uint32_t n = ip - next_emit;
-      if (op + literal_size(n) > abort_thr) return kAborted;
-      op += thread_emit_literal(out + op, v, next_emit, n);
-    }
-    for (;;) {
-      uint32_t matched = 4 + thread_match_len(v, len, cand + 4, ip + 4);
-      op += thread_emit_copy(out + op, ip - cand, matched);
-      ip += matched;
-      if (op > abort_thr) return kAborted;
-      if (ip > ip_limit) {
-        if (ip < len) {
-          uint32_t n = len - ip;
-          if (op + literal_size(n) > abort_thr) return kAborted;
-          op += thread_emit_literal(out + op, v, ip, n);
+  };
+
+  while (mode != kTDone) {
+    const bool probing = mode <= kTChain;
+    const uint32_t pa = probing ? ip - 1 : e_s2;
+    const uint32_t pb = mode == kTScan ? next_emit : (mode == kTExtend ? e_s1 : lit_src);
+    uint32_t a0, a1, a2, b0, b1, b2, b3;
+    in_ld12(v, pa, a0, a1, a2);
+    in_ld16(v, pb, b0, b1, b2, b3);
+    if (probing) {
+      const uint32_t d = __funnelshift_r(a0, a1, 8), dhi = __funnelshift_r(a1, a2, 8);
+      if (mode == kTChain) table[hash14(a0, mask)] = (uint16_t)(ip - 1);   // :371
+      const uint32_t h = hash14(d, mask);
+      const uint32_t cand = table[h];                                      // :293 / :375
+      table[h] = (uint16_t)ip;                                             // :294 / :377
+      uint32_t c_lo, c_hi;
+      in_ld8(v, cand, c_lo, c_hi);
+      const uint32_t x_lo = d ^ c_lo, x_hi = dhi ^ c_hi;
+      const uint32_t ml = x_lo ? first_diff_byte(x_lo) : (x_hi ? 4 + first_diff_byte(x_hi) : 8);
+      if (ml >= 4) {
+        if (mode == kTScan) {                                              // :336-338
+          const uint32_t n = ip - next_emit;
+          if (op + literal_size(n) > abort_thr) { aborted = true; mode = kTDone; continue; }
+          op += tw_literal_tag(wr, n) + n;
+          if (n > 16) { lit_src = next_emit; lit_n = n; pend_cand = cand; pend_ml = ml; mode = kTLit; continue; }
+          tw_put16(wr, n, b0, b1, b2, b3);
         }
-        return op;
+        begin_copy(cand, ml);
+      } else if (mode == kTScan) {
+        ip = next_ip;
+        arm_scan();
+      } else {                                                             // :379-380 -> :255-258
+        next_emit = ip; ip += 1; skip = 32;
+        arm_scan();
       }
-      uint32_t d1, dhi;
-      in_ld8(v, ip - 1, d1, dhi);
-      uint32_t d = __funnelshift_r(d1, dhi, 8);
-      table[hash14(d1, mask)] = (uint16_t)(ip - 1);
-      uint32_t h = hash14(d, mask);
-      cand = table[h];
-      table[h] = (uint16_t)ip;
-      if (in_ld4(v, cand) != d) break;
+    } else if (mode == kTExtend) {
+      const uint32_t rem = len - e_s2;
+      const uint32_t x0 = a0 ^ b0, x1 = a1 ^ b1, x2 = a2 ^ b2;
+      uint32_t k = x0 ? first_diff_byte(x0) : (x1 ? 4 + first_diff_byte(x1) : (x2 ? 8 + first_diff_byte(x2) : 12));
+      k = umin32(k, rem);
+      e_matched += k;
+      if (k == 12) { e_s1 += 12; e_s2 += 12; continue; }
+      op += tw_copy(wr, e_off, e_matched);
+      after_copy(e_matched);
+    } else {  // kTLit
+      const uint32_t k = umin32(16, lit_n);
+      tw_put16(wr, k, b0, b1, b2, b3);
+      lit_src += k; lit_n -= k;
+      if (lit_n == 0) {
+        if (pend_ml) begin_copy(pend_cand, pend_ml); else mode = kTDone;
+      }
     }
   }
+  return aborted ? kAborted : op;
 }
 
 struct CompressTArgs {
   const uint8_t* in_base;   // contiguous stream, block i = bytes [65536 i, ...)
-  uint8_t* out_base;        // scratch slots
+  uint8_t* out_base;        // scratch slots (4-byte aligned, stride a multiple of 4)
   uint16_t* tables;         // count x 16384 entries, zeroed
   uint64_t total_len;
   uint64_t out_stride;
@@ -863,34 +1253,34 @@ struct CompressTArgs {
 };
 // Frames: stored chunks only get their 8-byte header here; compact_kernel takes the payload
 // straight from the input (slot[0] == 0x01 marks them).
-__global__ void __launch_bounds__(64) compress_thread_kernel(CompressTArgs a) {
+__global__ void __launch_bounds__(32) compress_thread_kernel(CompressTArgs a) {
   uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
   if (job >= a.count) return;
   uint64_t ioff = (uint64_t)job * kMaxBlock;
   uint32_t len = (uint32_t)((a.total_len - ioff) < kMaxBlock ? (a.total_len - ioff) : kMaxBlock);
   const uint8_t* in = a.in_base + ioff;
-  uint8_t* out = a.out_base + (uint64_t)job * a.out_stride;
+  uint32_t* slot = (uint32_t*)(a.out_base + (uint64_t)job * a.out_stride);
   uint16_t* table = a.tables + (size_t)job * kMaxTableEntries;
   uint32_t total;
-  if (a.mode == kModeFrame) {
-    uint32_t crc = a.crc[job];
+  TWriter wr;
+  wr.hi = 0;
+  if (a.mode == kModeFrame) {  // encoder.nim:385-426
     uint32_t hl = varint32_len(len), thr = len - len / 8, bl = kAborted, fl;
-    if (len >= kMinNonLiteral) bl = compress_block_thread(in, len, out + 8 + hl, table, thr);
-    if (bl != kAborted && bl <= thr) {
-      uint32_t x = len, i = 0;
-      while (x >= 0x80) { out[8 + i++] = (uint8_t)(x | 0x80); x >>= 7; }
-      out[8 + i] = (uint8_t)x;
-      fl = hl + bl + 4;
-      out[0] = 0x00;
-    } else {
-      fl = len + 4;
-      out[0] = 0x01;
-    }
-    out[1] = (uint8_t)fl; out[2] = (uint8_t)(fl >> 8); out[3] = (uint8_t)(fl >> 16);
-    out[4] = (uint8_t)crc; out[5] = (uint8_t)(crc >> 8); out[6] = (uint8_t)(crc >> 16); out[7] = (uint8_t)(crc >> 24);
+    // the block starts right after the 8-byte frame header and the varint: seed the writer with the varint
+    uint32_t vb = 0;
+    { uint32_t x = len, i = 0; while (x >= 0x80) { vb |= ((x & 0x7f) | 0x80) << (8 * i++); x >>= 7; } vb |= x << (8 * i); }
+    wr.w = slot + 2; wr.lo = vb; wr.fill = hl;
+    if (len >= kMinNonLiteral) bl = compress_block_thread(in, len, wr, table, thr);
+    uint32_t type = 0x01;
+    if (bl != kAborted && bl <= thr) { fl = hl + bl + 4; type = 0x00; tw_flush(wr); }
+    else fl = len + 4;
+    slot[0] = type | (fl << 8);
+    slot[1] = a.crc[job];
     total = fl + 4;
   } else {
-    total = compress_block_thread(in, len, out, table, kNoAbort);
+    wr.w = slot; wr.lo = 0; wr.fill = 0;
+    total = compress_block_thread(in, len, wr, table, kNoAbort);
+    tw_flush(wr);
   }
   a.out_len[job] = total;
 }
