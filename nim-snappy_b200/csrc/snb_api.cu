@@ -84,8 +84,8 @@ struct Ctx {
   float prof[6] = {0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
   uint32_t call_launches = 0;
-  int compress_warps = 7;    // 64 KiB blocks: encoder warps per SM with the table in shared memory
-  int compress_gwarps = 14;  // ... and with the table in global memory (L2)
+  int compress_warps = 4;    // 64 KiB blocks: encoder warps per SM with the table in shared memory
+  int compress_gwarps = 16;  // ... and with the table in global memory (L2)
   int compress_algo = 0;  // 0 auto, 1/2/4 warp encoders v1/v2/v3, 3 one thread per block
   int thread_min_chunks = 1 << 30;  // auto mode: batches at least this large use one thread per block (tables in HBM)
   std::string err;
@@ -896,5 +896,10 @@ uint64_t snb_kernel_launches(void) { return g.launches; }
 void snb_set_compress_warps(int warps) { g.compress_warps = warps % 100; if (warps >= 100) g.compress_gwarps = warps / 100 - 1; }
 void snb_set_compress_algo(int algo) { g.compress_algo = algo; }
 void snb_set_thread_min_chunks(int n) { g.thread_min_chunks = n; }
+#ifdef SNB_STATS
+void snb_debug_stats(unsigned long long* out, int reset) {
+  for (int i = 0; i < 16; i++) { out[i] = snb::g_stats[i]; if (reset) snb::g_stats[i] = 0; }
+}
+#endif
 
 }  // extern "C"

@@ -37,6 +37,14 @@ enum : int32_t { kOk = 0, kBufferTooSmall = 1, kInvalidInput = 2, kCrcMismatch =
 enum : uint32_t { kModeFrame = 0, kModeRawBlock = 1, kModeRawMessage = 2 };
 enum : uint32_t { kKindCompressed = 0, kKindStored = 1, kKindVerifyOnly = 2 };
 
+// Optional event counters for tuning (tests/emu builds with -DSNB_STATS; never in the product build).
+#ifdef SNB_STATS
+__device__ unsigned long long g_stats[16];
+#define SNB_STAT(i) do { if (lane == 0) atomicAdd(&g_stats[i], 1ull); } while (0)
+#else
+#define SNB_STAT(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
@@ -687,12 +695,22 @@ __device__ __forceinline__ void in_ld12u(const InView& v, uint32_t p, uint32_t& 
   uint32_t w0 = __ldg(v.w + k), w1 = __ldg(v.w + k + 1), w2 = __ldg(v.w + k + 2), w3 = __ldg(v.w + umin32(k + 3, v.last));
   b0 = __funnelshift_r(w0, w1, s); b1 = __funnelshift_r(w1, w2, s); b2 = __funnelshift_r(w2, w3, s);
 }
-__device__ __forceinline__ void win_fetch(const InView& v, const uint16_t* table, uint32_t mask, uint32_t p, WinData& w) {
-  in_ld12u(v, p, w.a0, w.a1, w.a2);
+// The four aligned words holding in[p .. p+12), left unshifted so that issuing the loads does not wait for them.
+struct Raw4 { uint32_t w0, w1, w2, w3; };
+__device__ __forceinline__ void in_ld_raw(const InView& v, uint32_t p, Raw4& r) {
+  uint32_t k = (p + v.mis) >> 2;
+  r.w0 = __ldg(v.w + k); r.w1 = __ldg(v.w + k + 1); r.w2 = __ldg(v.w + k + 2); r.w3 = __ldg(v.w + umin32(k + 3, v.last));
+}
+__device__ __forceinline__ void raw_to12(const InView& v, uint32_t p, const Raw4& r, uint32_t& b0, uint32_t& b1, uint32_t& b2) {
+  uint32_t s = ((p + v.mis) & 3) * 8;
+  b0 = __funnelshift_r(r.w0, r.w1, s); b1 = __funnelshift_r(r.w1, r.w2, s); b2 = __funnelshift_r(r.w2, r.w3, s);
+}
+__device__ __forceinline__ void win_load_a(const InView& v, uint32_t p, WinData& w) { in_ld12u(v, p, w.a0, w.a1, w.a2); }
+__device__ __forceinline__ void win_load_t(const uint16_t* table, uint32_t mask, WinData& w) {
   w.h = hash14(w.a0, mask);
   w.T = table[w.h];
-  in_ld12u(v, w.T, w.c0, w.c1, w.c2);
 }
+__device__ __forceinline__ void win_load_c(const InView& v, WinData& w) { in_ld12u(v, w.T, w.c0, w.c1, w.c2); }
 
 __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict__ in, uint32_t len,
                                                       uint8_t* __restrict__ out, uint16_t* table,
@@ -720,8 +738,10 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
   uint32_t k = 0;           // literal mode: probes already done in this run
   bool chain = false, force_slow = false;
   bool m1_done = false;     // chain mode, ip on a window boundary: ip-1 has already been inserted
-  WinData cur, nxt;
-  uint32_t cur_b = 0xffffffffu, nxt_b = 0xffffffffu;
+  constexpr uint32_t kNoWindow = 0xffffffffu;
+  WinData cur, n1, n2;       // n1 / n2 only carry (a, h, T)
+  Raw4 n1c, n3a;             // candidate words of n1, own words of the window after n2 (loads in flight)
+  uint32_t cur_b = kNoWindow, n1_b = kNoWindow, n2_b = kNoWindow, n3_b = kNoWindow;
 
 #define SNB_FINISH(from)                                                          \
   do {                                                                            \
@@ -739,9 +759,11 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
     const uint32_t b = (chain ? ip : pp) & ~31u;
 
     if (force_slow || b + 32 >= ip_limit || (!chain && k >= 32)) {
+      SNB_STAT(force_slow ? 1 : ((b + 32 >= ip_limit) ? 2 : 3));
       force_slow = false;
       m1_done = false;
       if (chain) {
+        SNB_STAT(4);
         // ---- one serial chain step straight on the table (encoder.nim:364-380)
         const uint32_t d1 = in_ld4(v, ip - 1), d = in_ld4(v, ip);
         const uint32_t h1 = hash14(d1, mask), hh = hash14(d, mask);
@@ -758,6 +780,7 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
         continue;
       }
       // ---- serial literal scan from (pp, k): 32 strided probes per step (encoder.nim:281-331)
+      SNB_STAT(5);
       uint32_t wip = pp, wskip = 32 + k;
       uint32_t hit_ip = 0, hit_cand = 0;
       bool found = false;
@@ -807,6 +830,7 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
     }
 
     // ---- window data for [b, b+32): every lane is a valid lookup position (b + 32 < ip_limit)
+    SNB_STAT(0);
     const uint32_t p = b + lane;
     if (chain && ip == b && !m1_done) {  // arrival on the window boundary after a serial step: ip-1 is not a lane here
       const uint32_t d1 = in_ld4(v, ip - 1);
@@ -814,15 +838,40 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
       __syncwarp();
     }
     m1_done = false;
-    if (cur_b != b) {
-      if (nxt_b == b) cur = nxt; else win_fetch(v, table, mask, p, cur);
+    const bool fresh = cur_b != b;
+    const bool seq = n1_b == b;
+    if (fresh) {
+      if (seq) {
+        cur.a0 = n1.a0; cur.a1 = n1.a1; cur.a2 = n1.a2; cur.h = n1.h; cur.T = n1.T;
+        raw_to12(v, n1.T, n1c, cur.c0, cur.c1, cur.c2);
+      } else {
+        win_load_a(v, p, cur); win_load_t(table, mask, cur); win_load_c(v, cur);
+      }
       cur_b = b;
     }
-    {  // re-validate against the committed table
-      const uint32_t T = table[cur.h];
-      if (T != cur.T) { cur.T = T; in_ld12u(v, T, cur.c0, cur.c1, cur.c2); }
+    const uint32_t Tnow = table[cur.h];   // re-validation against the committed table (consumed below)
+    if (fresh) {
+      // Software pipeline over windows, one stage per pass; loaded words stay raw (unshifted) until
+      // the next pass so that nothing waits for a load in the pass that issued it:
+      //   own words (b+96) -> own bytes, hash, table entry (b+64) -> candidate words (b+32).
+      const bool seq2 = seq && n2_b == b + 32, seq3 = seq && n3_b == b + 64;
+      if (b + 64 < ip_limit) {
+        if (seq2) { n1.a0 = n2.a0; n1.a1 = n2.a1; n1.a2 = n2.a2; n1.h = n2.h; n1.T = n2.T; }
+        else { win_load_a(v, p + 32, n1); win_load_t(table, mask, n1); }
+        in_ld_raw(v, n1.T, n1c);
+        n1_b = b + 32;
+      } else n1_b = kNoWindow;
+      if (b + 96 < ip_limit) {
+        if (seq3) raw_to12(v, p, n3a, n2.a0, n2.a1, n2.a2); else win_load_a(v, p + 64, n2);
+        win_load_t(table, mask, n2);
+        n2_b = b + 64;
+      } else n2_b = kNoWindow;
+      if (b + 128 < ip_limit) { in_ld_raw(v, p + 96, n3a); n3_b = b + 96; } else n3_b = kNoWindow;
     }
-    if (nxt_b != b + 32 && b + 64 < ip_limit) { win_fetch(v, table, mask, p + 32, nxt); nxt_b = b + 32; }
+#ifdef SNB_STATS
+    if (__ballot_sync(kFull, Tnow != cur.T)) SNB_STAT(10);
+#endif
+    if (Tnow != cur.T) { cur.T = Tnow; in_ld12u(v, Tnow, cur.c0, cur.c1, cur.c2); }
 
     // ---- resolve
     const uint32_t x0 = cur.a0 ^ cur.c0, x1 = cur.a1 ^ cur.c1, x2 = cur.a2 ^ cur.c2;
@@ -838,7 +887,8 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
     const uint32_t HB = __ballot_sync(kFull, hit);
 
     uint32_t ins = 0;   // lanes inserted (accepted) in this pass
-    uint32_t c0;        // first chain-arrival lane of this pass (>= 32: outside the window)
+    uint32_t c0;        // next chain-arrival lane (>= 32: outside the window)
+    bool done = false;  // block finished inside this pass (ip > ip_limit after a copy)
     if (!chain) {
       // ---- the literal run entering the window: stride-1 probes at lanes [l0, bend)
       const uint32_t l0 = pp - b;
@@ -846,38 +896,46 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
       const uint32_t range = (0xffffffffu << l0) & (bend >= 32 ? 0xffffffffu : ((1u << bend) - 1u));
       const uint32_t qh = HB & range;
       const uint32_t q0 = qh ? (uint32_t)__ffs((int)qh) - 1u : 32u;
-      const uint32_t run = range & ((2u << (q0 & 31)) - 1u | (q0 >= 32 ? 0xffffffffu : 0u));   // probes performed
+      const uint32_t run = range & (((2u << (q0 & 31)) - 1u) | (q0 >= 32 ? 0xffffffffu : 0u));   // probes performed
       const uint32_t stale = __ballot_sync(kFull, (eg & run) != 0) & run;
-      const uint32_t q0rec = __shfl_sync(kFull, rec, (int)(q0 & 31));
-      const uint32_t q0ml = q0rec >> 25;
-      if (stale || (q0 < 32 && q0ml >= 12)) { force_slow = true; continue; }
+      if (stale) { SNB_STAT(6); force_slow = true; continue; }
       if (q0 >= 32) {  // every probe missed: insert them and move on (k == 32 switches to the strided scan)
         if (((run >> lane) & 1u) && ((grp & run) >> lane) == 1u) table[cur.h] = (uint16_t)p;
         k += (uint32_t)__popc(run);
         pp = b + bend;
         continue;
       }
+      const uint32_t q0rec = __shfl_sync(kFull, rec, (int)q0);
+      const uint32_t q0ml = q0rec >> 25;
       {  // :336-338, then the copy at q0
         const uint32_t n = b + q0 - next_emit;
         if (op + literal_size(n) > abort_thr) return kAborted;
         op += emit_literal_v2(out + op, v, next_emit, n, lane);
+      }
+      ins = run;
+      chain = true;
+      if (q0ml >= 12) {  // the match reaches the horizon: measure it (encoder.nim:130-182)
+        SNB_STAT(7);
+        const uint32_t cand = __shfl_sync(kFull, cur.T, (int)q0);
+        const uint32_t m = 12 + common_prefix_v2(v, len, cand + 12, b + q0 + 12, lane);
+        op += emit_copy_v2(out + op, b + q0 - cand, m, lane);
+        ip = b + q0 + m;
+      } else {
         if (lane == 0) {
           uint8_t* o = out + op;
           o[0] = (uint8_t)q0rec; o[1] = (uint8_t)(q0rec >> 8);
           if ((q0rec >> 24) & 1u) o[2] = (uint8_t)(q0rec >> 16);
         }
         op += ((q0rec >> 24) & 1u) ? 3u : 2u;
+        ip = b + q0 + q0ml;
       }
-      ins = run;
-      chain = true;
-      c0 = q0 + q0ml;
-      ip = b + c0;
+      if (ip > ip_limit) done = true;
+      c0 = ip - b;
     } else {
       c0 = ip - b;
     }
 
-    bool pend_insert = false;
-    if (c0 < 32) {
+    if (c0 < 32 && !done) {
       // ---- every lane as a chain arrival: its event lane, the next arrival, its output size
       const uint32_t qb = hit ? (1u << lane) : (HB & above);
       const uint32_t evt = qb ? (uint32_t)__ffs((int)qb) - 1u : 32u;
@@ -886,61 +944,84 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
       const uint32_t J0 = evt < 32 ? evt + eml : 64u;   // >= 32 leaves the window, 64: in literal mode
       const uint32_t litn = evt - lane;
       const uint32_t sz = evt < 32 ? (hit ? 0u : litn + 1u) + (((erec >> 24) & 1u) ? 3u : 2u) : 0u;
-      uint32_t J = J0, D = sz, R = 1u << c0;
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-        const uint32_t contrib = (((R >> lane) & 1u) && J < 32) ? (1u << J) : 0u;
-        R |= __reduce_or_sync(kFull, contrib);
-        const uint32_t jn = __shfl_sync(kFull, J, (int)(J & 31));
-        const uint32_t dn = __shfl_sync(kFull, D, (int)(J & 31));
-        if (J < 32) { D += dn; J = jn; }
-      }
-      const bool onp = (R >> lane) & 1u;
       // inserts of a node: ip-1, ip, then the probes up to its event (encoder.nim:371-377, :293-294)
       const uint32_t nmask = (0xffffffffu << (lane ? lane - 1 : 0)) & ((2u << (evt < 32 ? evt : 31u)) - 1u);
-      const uint32_t ins_all = ins | __reduce_or_sync(kFull, onp ? nmask : 0u);
-      const uint32_t stale = __ballot_sync(kFull, (eg & ins_all) != 0) & ins_all;
-      const bool mybad = onp && (((stale & nmask) != 0) || (evt < 32 && eml >= 12));
-      const uint32_t BAD = __ballot_sync(kFull, mybad);
-      const uint32_t cb = BAD ? (uint32_t)__ffs((int)BAD) - 1u : 32u;
-      const uint32_t ACC = R & (cb >= 32 ? 0xffffffffu : ((1u << cb) - 1u));
-      const bool acc = (ACC >> lane) & 1u;
-      ins = BAD ? (ins | __reduce_or_sync(kFull, acc ? nmask : 0u)) : ins_all;
-      const uint32_t Dc0 = __shfl_sync(kFull, D, (int)c0);
-      const uint32_t Dcb = __shfl_sync(kFull, D, (int)(cb & 31));
-      const uint32_t off_me = op + (Dc0 - D);           // output offset of my node (accepted lanes)
-      if (acc && evt < 32) {
-        uint8_t* o = out + off_me;
-        if (!hit) { o[0] = (uint8_t)((litn - 1) << 2); o += 1 + litn; }
-        o[0] = (uint8_t)erec; o[1] = (uint8_t)(erec >> 8);
-        if ((erec >> 24) & 1u) o[2] = (uint8_t)(erec >> 16);
-      }
-      {  // literal bytes: lanes from a missed accepted node up to its event write their own byte
-        const uint32_t nm = ACC & ((2u << lane) - 1u);
-        const uint32_t node = nm ? 31u - (uint32_t)__clz((int)nm) : 0u;
-        const uint32_t pk = __shfl_sync(kFull, off_me | (evt << 20) | (hit ? 1u << 26 : 0u), (int)node);
-        const uint32_t ev = (pk >> 20) & 63u;
-        if (nm && !((pk >> 26) & 1u) && ev < 32 && lane < ev) out[(pk & 0xfffffu) + 1 + (lane - node)] = (uint8_t)cur.a0;
-      }
-      op += Dc0 - (BAD ? Dcb : 0u);
-      if (BAD) {
-        ip = b + cb; force_slow = true;
-      } else {
-        const uint32_t cl = 31u - (uint32_t)__clz((int)R);
-        const uint32_t Jl = __shfl_sync(kFull, J0, (int)cl);
-        if (Jl == 64u) { chain = false; next_emit = b + cl; pp = b + 32; k = 31 - cl; }
-        else ip = b + Jl;
+      const bool elong = evt < 32 && eml >= 12;
+      for (;;) {
+        uint32_t J = J0, D = sz, R = 1u << c0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          const uint32_t contrib = (((R >> lane) & 1u) && J < 32) ? (1u << J) : 0u;
+          R |= __reduce_or_sync(kFull, contrib);
+          const uint32_t jn = __shfl_sync(kFull, J, (int)(J & 31));
+          const uint32_t dn = __shfl_sync(kFull, D, (int)(J & 31));
+          if (J < 32) { D += dn; J = jn; }
+        }
+        const bool onp = (R >> lane) & 1u;
+        const uint32_t ins_all = ins | __reduce_or_sync(kFull, onp ? nmask : 0u);
+        const uint32_t stale = __ballot_sync(kFull, (eg & ins_all) != 0) & ins_all;
+        const bool mystale = (stale & nmask) != 0;
+        const uint32_t BAD = __ballot_sync(kFull, onp && (mystale || elong));
+        const uint32_t cb = BAD ? (uint32_t)__ffs((int)BAD) - 1u : 32u;
+        const uint32_t ACC = R & (cb >= 32 ? 0xffffffffu : ((1u << cb) - 1u));
+        const bool acc = (ACC >> lane) & 1u;
+        // what stops the accepted prefix: a stale lookup (serial step) or only the 12-byte horizon (measured here)
+        const bool cb_long = BAD && !__shfl_sync(kFull, (uint32_t)mystale, (int)(cb & 31));
+        const uint32_t take = cb_long ? (ACC | (1u << cb)) : ACC;    // nodes whose inserts are performed
+        ins = BAD ? (ins | __reduce_or_sync(kFull, ((take >> lane) & 1u) ? nmask : 0u)) : ins_all;
+        const uint32_t Dc0 = __shfl_sync(kFull, D, (int)c0);
+        const uint32_t Dcb = __shfl_sync(kFull, D, (int)(cb & 31));
+        const uint32_t off_me = op + (Dc0 - D);           // output offset of my node (accepted lanes)
+        if (acc && evt < 32) {
+          uint8_t* o = out + off_me;
+          if (!hit) { o[0] = (uint8_t)((litn - 1) << 2); o += 1 + litn; }
+          o[0] = (uint8_t)erec; o[1] = (uint8_t)(erec >> 8);
+          if ((erec >> 24) & 1u) o[2] = (uint8_t)(erec >> 16);
+        }
+        {  // literal bytes: lanes from a missed node up to its event write their own byte
+          const uint32_t nm = take & ((2u << lane) - 1u);
+          const uint32_t node = nm ? 31u - (uint32_t)__clz((int)nm) : 0u;
+          const uint32_t pk = __shfl_sync(kFull, off_me | (evt << 20) | (hit ? 1u << 26 : 0u), (int)node);
+          const uint32_t ev = (pk >> 20) & 63u;
+          if (nm && !((pk >> 26) & 1u) && ev < 32 && lane < ev) out[(pk & 0xfffffu) + 1 + (lane - node)] = (uint8_t)cur.a0;
+        }
+        op += Dc0 - (BAD ? Dcb : 0u);
+        if (!BAD) {
+          const uint32_t cl = 31u - (uint32_t)__clz((int)R);
+          const uint32_t Jl = __shfl_sync(kFull, J0, (int)cl);
+          if (Jl == 64u) { chain = false; next_emit = b + cl; pp = b + 32; k = 31 - cl; }
+          else ip = b + Jl;
+          break;
+        }
+        SNB_STAT(8);
+        if (!cb_long) { SNB_STAT(9); ip = b + cb; force_slow = true; break; }
+        // ---- node cb: (literal,) then a copy of at least 12 bytes, measured with the whole warp
+        const uint32_t pkb = __shfl_sync(kFull, evt | (hit ? 32u : 0u), (int)cb);
+        const uint32_t ev = pkb & 31u;
+        if (!(pkb & 32u)) {  // literal tag of the missed node (its bytes were written above)
+          if (lane == 0) out[op] = (uint8_t)((ev - cb - 1) << 2);
+          op += 1 + (ev - cb);
+        }
+        const uint32_t cand = __shfl_sync(kFull, cur.T, (int)ev);
+        const uint32_t m = 12 + common_prefix_v2(v, len, cand + 12, b + ev + 12, lane);
+        op += emit_copy_v2(out + op, b + ev - cand, m, lane);
+        ip = b + ev + m;
+        if (ip > ip_limit) { done = true; break; }
+        c0 = ip - b;
+        if (c0 >= 32) break;
       }
     }
+    if (chain && !force_slow && ip > ip_limit) done = true;   // encoder.nim:362-363
     // the next arrival's ip-1 insert when no window pass will own it (lane c-1 of the node rule)
-    if (chain && !force_slow && (ip & 31u) == 0 && ip <= ip_limit) {
+    bool pend_insert = false;
+    if (chain && !force_slow && !done && (ip & 31u) == 0) {
       if (ip == b + 32) ins |= 1u << 31; else pend_insert = true;
       m1_done = true;
     }
     // ---- commit: the last inserted lane of each hash group writes the table
     if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[cur.h] = (uint16_t)p;
     if (op > abort_thr) return kAborted;
-    if (chain && ip > ip_limit) SNB_FINISH(ip);
+    if (done) SNB_FINISH(ip);
     if (pend_insert) {
       __syncwarp();
       const uint32_t d1 = in_ld4(v, ip - 1);
@@ -1033,9 +1114,9 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
 // pointer is generic.  The extra warps are what fills the issue slots: one encoder warp is a
 // single dependent chain.
 #ifndef SNB_COMPRESS_MAXT
-#define SNB_COMPRESS_MAXT 768
+#define SNB_COMPRESS_MAXT 640
 #endif
-constexpr uint32_t kCompressMaxThreads = SNB_COMPRESS_MAXT;  // register budget: 65536 / 768 = 85 per thread
+constexpr uint32_t kCompressMaxThreads = SNB_COMPRESS_MAXT;  // register budget: 65536 / 640 = 102 per thread (no spills: spilled prefetch registers stall on their loads)
 __global__ void __launch_bounds__(kCompressMaxThreads, 1) compress_kernel(CompressArgs a) {
   SNB_DYN_SMEM(smem);
   uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
