@@ -32,7 +32,7 @@ constexpr uint64_t kChunk = snb::kMaxBlock;
 constexpr uint64_t kFrameStride = 65664;           // >= 65544 (stored frame) and >= the abort bound, multiple of 128
 constexpr uint64_t kRawStride = 76544;             // >= maxCompressedLen(65536) = 76490, multiple of 128
 constexpr uint32_t kDevSlabChunks = 16384;         // 1 GiB of input per device-side slab
-constexpr uint32_t kHostSlabChunks = 1024;         // 64 MiB of input per host<->device slab
+constexpr uint32_t kHostSlabChunks = 4096;         // 256 MiB of input per host<->device slab (fills 148 SMs x 20 encoder warps)
 constexpr int kNumCounters = 256;
 const uint8_t kStreamHeader[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};  // codec.nim:33-34
 
