@@ -84,8 +84,8 @@ struct Ctx {
   float prof[6] = {0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
   uint32_t call_launches = 0;
-  int compress_warps = 4;    // 64 KiB blocks: encoder warps per SM with the table in shared memory
-  int compress_gwarps = 16;  // ... and with the table in global memory (L2)
+  int compress_warps = 0;    // 64 KiB blocks: encoder warps per SM with the table in shared memory
+  int compress_gwarps = 20;  // ... and with the table in global memory (L2 resident; leaves the SM its whole L1)
   int compress_algo = 0;  // 0 auto, 1/2/4 warp encoders v1/v2/v3, 3 one thread per block
   int thread_min_chunks = 1 << 30;  // auto mode: batches at least this large use one thread per block (tables in HBM)
   std::string err;
@@ -243,12 +243,13 @@ CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
     cg.smem_warps = (uint32_t)std::max(0, std::min(7, g.compress_warps));
     uint32_t extra = (uint32_t)std::max(0, std::min((int)(snb::kCompressMaxThreads / 32 - cg.smem_warps), g.compress_gwarps));
     cg.warps = std::max(1u, cg.smem_warps + extra);
+    while (cg.smem_warps > 0 && cg.smem_warps * tbytes + cg.warps * snb::kStageWords * 4 > 227 * 1024) { cg.smem_warps--; cg.warps--; }
     ctas_per_sm = 1;
   } else {
     cg.warps = cg.smem_warps = 8;
-    ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (cg.warps * tbytes + 1024)));
+    ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (cg.warps * (tbytes + snb::kStageWords * 4) + 1024)));
   }
-  cg.smem = cg.smem_warps * tbytes;
+  cg.smem = cg.smem_warps * tbytes + cg.warps * snb::kStageWords * 4;  // tables, then the v3 encoder's staging area
   uint32_t need = (count + cg.warps - 1) / cg.warps;
   cg.grid = std::max(1u, std::min(need, (uint32_t)g.sms * ctas_per_sm));
   return cg;

@@ -50,6 +50,21 @@ __device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > 
 
 // index of the lowest non-zero byte of x (x != 0)
 __device__ __forceinline__ uint32_t first_diff_byte(uint32_t x) { return (uint32_t)(__ffs((int)x) - 1) >> 3; }
+// Asynchronous 4-byte global -> shared copies (LDGSTS): completion is tracked per commit group, not by a
+// register scoreboard, so a copy issued in one pass of a long loop can be consumed a pass later without
+// the consumer also waiting for younger loads that happen to share a scoreboard slot.
+#ifdef SNB_EMULATE
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) { *smem_dst = *gsrc; }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#endif
 // Unaligned little-endian 32-bit load built from aligned words.  Only words holding at least
 // one requested byte are touched.
 __device__ __forceinline__ uint32_t load32u(const uint8_t* p) {
@@ -712,9 +727,12 @@ __device__ __forceinline__ void win_load_t(const uint16_t* table, uint32_t mask,
 }
 __device__ __forceinline__ void win_load_c(const InView& v, WinData& w) { in_ld12u(v, w.T, w.c0, w.c1, w.c2); }
 
+constexpr uint32_t kStageWords = 352;   // per-warp staging in shared memory: own[2][16] + tab[2][32] + cand[2][4][32]
 __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict__ in, uint32_t len,
                                                       uint8_t* __restrict__ out, uint16_t* table,
-                                                      uint32_t abort_thr, uint32_t lane) {
+                                                      uint32_t abort_thr, uint32_t lane, uint32_t stage_idx, bool tglobal) {
+  SNB_DYN_SMEM(smem_raw);
+  uint32_t* const stage = (uint32_t*)smem_raw + stage_idx;   // 32-bit index arithmetic on the shared window
   InView v;
   v.mis = (uint32_t)((uintptr_t)in & 3);
   v.w = (const uint32_t*)(in - v.mis);
@@ -740,7 +758,11 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
   bool m1_done = false;     // chain mode, ip on a window boundary: ip-1 has already been inserted
   constexpr uint32_t kNoWindow = 0xffffffffu;
   WinData cur, n1, n2;       // n1 / n2 only carry (a, h, T)
-  Raw4 n1c, n3a;             // candidate words of n1, own words of the window after n2 (loads in flight)
+  // staging (shared memory, filled by cp.async one pass before it is read; slot = window index & 1)
+  uint32_t* const st_own = stage;          // [2][16]: the 12 aligned words holding a window's 44 bytes
+  uint32_t* const st_tab = stage + 32;     // [2][32]: the aligned word holding each lane's table entry
+  uint32_t* const st_cand = stage + 96;    // [2][4][32]: four aligned words at each lane's candidate
+  const uint32_t own_q = (lane + v.mis) >> 2, own_s = ((lane + v.mis) & 3) * 8;
   uint32_t cur_b = kNoWindow, n1_b = kNoWindow, n2_b = kNoWindow, n3_b = kNoWindow;
 
 #define SNB_FINISH(from)                                                          \
@@ -838,35 +860,65 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
       __syncwarp();
     }
     m1_done = false;
+    // Software pipeline over windows, one stage per pass, staged through shared memory by cp.async:
+    //   own words (b+96) -> own bytes, hash, table word (b+64) -> table entry, candidate words (b+32).
+    // A pass first consumes what the previous pass staged, then issues its own copies.
     const bool fresh = cur_b != b;
-    const bool seq = n1_b == b;
+    bool have1 = false, have2 = false, have3 = false;
+    const uint32_t wslot = (b >> 5) & 1u;
     if (fresh) {
+      const bool seq = n1_b == b;
+      const bool seq2 = seq && n2_b == b + 32, seq3 = seq && n3_b == b + 64;
+      cp_async_wait_all();
+      __syncwarp();
       if (seq) {
         cur.a0 = n1.a0; cur.a1 = n1.a1; cur.a2 = n1.a2; cur.h = n1.h; cur.T = n1.T;
-        raw_to12(v, n1.T, n1c, cur.c0, cur.c1, cur.c2);
+        const uint32_t* sc = st_cand + wslot * 128 + lane;
+        const uint32_t cs = ((n1.T + v.mis) & 3) * 8;
+        const uint32_t w0 = sc[0], w1 = sc[32], w2 = sc[64], w3 = sc[96];
+        cur.c0 = __funnelshift_r(w0, w1, cs); cur.c1 = __funnelshift_r(w1, w2, cs); cur.c2 = __funnelshift_r(w2, w3, cs);
       } else {
         win_load_a(v, p, cur); win_load_t(table, mask, cur); win_load_c(v, cur);
       }
       cur_b = b;
+      have1 = b + 64 < ip_limit; have2 = b + 96 < ip_limit; have3 = b + 128 < ip_limit;
+      if (have1) {
+        if (seq2) {
+          n1.a0 = n2.a0; n1.a1 = n2.a1; n1.a2 = n2.a2; n1.h = n2.h;
+          n1.T = tglobal ? ((st_tab[(wslot ^ 1u) * 32 + lane] >> ((n2.h & 1u) * 16)) & 0xffffu) : n2.T;
+        } else {
+          win_load_a(v, p + 32, n1); win_load_t(table, mask, n1);
+        }
+      }
+      if (have2) {
+        if (seq3) {
+          const uint32_t* so = st_own + wslot * 16 + own_q;
+          const uint32_t w0 = so[0], w1 = so[1], w2 = so[2], w3 = so[3];
+          n2.a0 = __funnelshift_r(w0, w1, own_s); n2.a1 = __funnelshift_r(w1, w2, own_s); n2.a2 = __funnelshift_r(w2, w3, own_s);
+        } else {
+          win_load_a(v, p + 64, n2);
+        }
+        n2.h = hash14(n2.a0, mask);
+      }
     }
     const uint32_t Tnow = table[cur.h];   // re-validation against the committed table (consumed below)
     if (fresh) {
-      // Software pipeline over windows, one stage per pass; loaded words stay raw (unshifted) until
-      // the next pass so that nothing waits for a load in the pass that issued it:
-      //   own words (b+96) -> own bytes, hash, table entry (b+64) -> candidate words (b+32).
-      const bool seq2 = seq && n2_b == b + 32, seq3 = seq && n3_b == b + 64;
-      if (b + 64 < ip_limit) {
-        if (seq2) { n1.a0 = n2.a0; n1.a1 = n2.a1; n1.a2 = n2.a2; n1.h = n2.h; n1.T = n2.T; }
-        else { win_load_a(v, p + 32, n1); win_load_t(table, mask, n1); }
-        in_ld_raw(v, n1.T, n1c);
+      if (have1) {
+        const uint32_t* src = v.w + ((n1.T + v.mis) >> 2);
+        uint32_t* sc = st_cand + (wslot ^ 1u) * 128 + lane;
+        cp_async4(sc, src); cp_async4(sc + 32, src + 1); cp_async4(sc + 64, src + 2); cp_async4(sc + 96, src + 3);
         n1_b = b + 32;
       } else n1_b = kNoWindow;
-      if (b + 96 < ip_limit) {
-        if (seq3) raw_to12(v, p, n3a, n2.a0, n2.a1, n2.a2); else win_load_a(v, p + 64, n2);
-        win_load_t(table, mask, n2);
+      if (have2) {
+        if (tglobal) cp_async4(st_tab + wslot * 32 + lane, (const uint32_t*)table + (n2.h >> 1));
+        else n2.T = table[n2.h];
         n2_b = b + 64;
       } else n2_b = kNoWindow;
-      if (b + 128 < ip_limit) { in_ld_raw(v, p + 96, n3a); n3_b = b + 96; } else n3_b = kNoWindow;
+      if (have3) {
+        if (lane < 12) cp_async4(st_own + (wslot ^ 1u) * 16 + lane, v.w + ((b + 96) >> 2) + lane);
+        n3_b = b + 96;
+      } else n3_b = kNoWindow;
+      cp_async_commit();
     }
 #ifdef SNB_STATS
     if (__ballot_sync(kFull, Tnow != cur.T)) SNB_STAT(10);
@@ -875,7 +927,12 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
 
     // ---- resolve
     const uint32_t x0 = cur.a0 ^ cur.c0, x1 = cur.a1 ^ cur.c1, x2 = cur.a2 ^ cur.c2;
-    const uint32_t ml = x0 ? first_diff_byte(x0) : (x1 ? 4 + first_diff_byte(x1) : (x2 ? 8 + first_diff_byte(x2) : 12));
+    uint32_t ml;
+    {  // common prefix of the 12 own / candidate bytes: one find-first-set on the first differing word
+      const uint32_t xs = x0 ? x0 : (x1 ? x1 : x2);
+      const uint32_t base = x0 ? 0u : (x1 ? 4u : 8u);
+      ml = xs ? base + first_diff_byte(xs) : 12u;
+    }
     const uint32_t off = p - cur.T;
     const bool c2 = off >= 2048;   // ml <= 11 whenever the tag is used (encoder.nim:113-125)
     const uint32_t tb = c2 ? ((((ml - 1) << 2) | 2u) | (off << 8))
@@ -1062,15 +1119,17 @@ __device__ __forceinline__ uint32_t varint32_len(uint32_t v) {
 }
 
 __device__ __forceinline__ uint32_t encode_block(uint32_t algo, const uint8_t* in, uint32_t len, uint8_t* out,
-                                                 uint16_t* table, uint32_t abort_thr, uint32_t lane) {
+                                                 uint16_t* table, uint32_t abort_thr, uint32_t lane, uint32_t stage,
+                                                 bool tglobal) {
   if (algo == 1) return compress_block_warp(in, len, out, table, abort_thr, lane);
   if (algo == 2) return compress_block_v2(in, len, out, table, abort_thr, lane);
-  return compress_block_v3(in, len, out, table, abort_thr, lane);
+  return compress_block_v3(in, len, out, table, abort_thr, lane, stage, tglobal);
 }
 
 // One job = one encodeFrame (encoder.nim:385-426), one bare encodeBlock, or one whole
 // single-block `compress` message (snappy.nim:27-64).
-__device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job, uint16_t* table, uint32_t lane) {
+__device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job, uint16_t* table, uint32_t lane,
+                                             uint32_t stage, bool tglobal) {
   uint64_t ioff = a.in_off ? a.in_off[job] : (uint64_t)job * kMaxBlock;
   uint32_t len = a.in_len ? a.in_len[job] : (uint32_t)((a.total_len - ioff) < kMaxBlock ? (a.total_len - ioff) : kMaxBlock);
   uint64_t ooff = a.out_off ? a.out_off[job] : (uint64_t)job * a.out_stride;
@@ -1082,7 +1141,7 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
   const uint32_t pre = frame ? 8u + hl : hl;
   const uint32_t thr = frame ? len - len / 8 : kNoAbort;
   uint32_t bl = frame ? kAborted : 0u;
-  if (frame ? len >= kMinNonLiteral : len > 0) bl = encode_block(a.algo, in, len, out + pre, table, thr, lane);  // encoder.nim:401-406
+  if (frame ? len >= kMinNonLiteral : len > 0) bl = encode_block(a.algo, in, len, out + pre, table, thr, lane, stage, tglobal);  // encoder.nim:401-406
   uint32_t total;
   if (frame) {
     uint32_t crc = a.crc[job];
@@ -1120,15 +1179,18 @@ constexpr uint32_t kCompressMaxThreads = SNB_COMPRESS_MAXT;  // register budget:
 __global__ void __launch_bounds__(kCompressMaxThreads, 1) compress_kernel(CompressArgs a) {
   SNB_DYN_SMEM(smem);
   uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint16_t* table = warp < a.smem_warps
+  const bool tglobal = warp >= a.smem_warps;
+  uint16_t* table = !tglobal
                         ? (uint16_t*)smem + (size_t)warp * a.table_entries
                         : a.gtables + ((size_t)blockIdx.x * (blockDim.x / 32 - a.smem_warps) + (warp - a.smem_warps)) * a.table_entries;
+  // per-warp staging area of the v3 encoder, behind the shared-memory tables
+  const uint32_t stage = a.smem_warps * a.table_entries / 2 + warp * kStageWords;   // word index into the dynamic shared memory
   for (;;) {
     uint32_t job = 0;
     if (lane == 0) job = atomicAdd(a.counter, 1u);
     job = __shfl_sync(kFull, job, 0);
     if (job >= a.count) return;
-    compress_job(a, job, table, lane);
+    compress_job(a, job, table, lane, stage, tglobal);
     __syncwarp();
   }
 }
