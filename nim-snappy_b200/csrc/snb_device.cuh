@@ -1559,34 +1559,48 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
   const uint32_t tn = n - br;
   const uint32_t lim = ulen;  // decisions are identical for any cap >= ulen
   uint32_t ip = 0, op = 0;
+  // aligned word view of the tag stream: word 0 holds tags[0] at byte `tmis`
+  const uint32_t tmis = (uint32_t)((uintptr_t)tags & 3);
+  const uint32_t* const tw = (const uint32_t*)(tags - tmis);
+  const uint32_t tw_last = (tn + tmis - 1) >> 2;   // tn >= 1 here
 
   while (ip < tn) {
     __syncwarp();  // output bytes of the previous step are visible to every lane
-    uint32_t pos = ip + lane;
-    bool inb = pos < tn;
-    uint32_t avail = inb ? tn - pos : 0;
-    uint32_t t = 0, v4 = 0;
-    if (inb) { t = tags[pos]; v4 = load_upto4(tags + pos + 1, umin32(avail - 1, 4)); }
-    uint32_t kind = t & 3, L, hdr = 1, off = 0, size;
-    bool bad = false;
+    // ---- the 36 stream bytes of this step: one aligned word per lane (0..10), then every lane
+    // assembles the 8 bytes starting at its own position through shuffles
+    const uint32_t i0 = ip + tmis;
+    const uint32_t W = __ldg(tw + umin32((i0 >> 2) + lane, tw_last));   // lanes >= 11 load a word nobody uses
+    const uint32_t q = ((i0 & 3) + lane) >> 2, sh = (((i0 & 3) + lane) & 3) * 8;
+    const uint32_t w0 = __shfl_sync(kFull, W, (int)q), w1 = __shfl_sync(kFull, W, (int)q + 1);
+    const uint32_t w2 = __shfl_sync(kFull, W, (int)q + 2);
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    const uint32_t pos = ip + lane;
+    const bool inb = pos < tn;
+    const uint32_t avail = inb ? tn - pos : 0;
+    const uint32_t t = lo & 0xff, v4 = __funnelshift_r(lo, hi, 8);   // bytes past `avail` are never used when !bad
+    const uint32_t kind = t & 3;
+    // ---- decode "a tag starting at my byte" (decoder.nim:39-109): L output bytes, `size` stream bytes
+    uint32_t L = (t >> 2) + 1, hdr = 1, off = 0, size;
+    bool bad;
     if (kind == 0) {
-      L = (t >> 2) + 1;
-      if (L >= 61) {                                           // decoder.nim:54-75
-        uint32_t ll = L - 60;
-        if (avail - 1 < 61) bad = true;
-        uint32_t m = ll == 4 ? 0xffffffffu : ((1u << (8 * ll)) - 1u);
+      size = 1 + L;
+      bad = avail < size;                                        // :77-79 (input side)
+      if (L >= 61) {                                             // :54-75
+        const uint32_t ll = L - 60;
+        bad = avail - 1 < 61;
+        const uint32_t m = ll == 4 ? 0xffffffffu : ((1u << (8 * ll)) - 1u);
         L = (v4 & m) + 1;
         if (L == 0) bad = true;
         hdr = 1 + ll;
+        if (!bad && avail - hdr < L) bad = true;
+        size = hdr + L;
       }
-      if (!bad && avail - hdr < L) bad = true;                 // :77-79 (input side)
-      size = hdr + L;
-    } else if (kind == 1) {                                    // :87-94
-      bad = avail < 2; L = 4 + ((t >> 2) & 7); off = ((t & 0xe0) << 3) | (v4 & 0xff); size = 2;
-    } else if (kind == 2) {                                    // :95-102
-      bad = avail < 3; L = 1 + (t >> 2); off = v4 & 0xffff; size = 3;
-    } else {                                                   // :103-109
-      bad = avail < 5; L = 1 + (t >> 2); off = v4; size = 5;
+    } else {
+      const bool k1 = kind == 1, k2 = kind == 2;
+      L = k1 ? 4 + ((t >> 2) & 7) : L;                           // :87-109
+      off = k1 ? (((t & 0xe0) << 3) | (v4 & 0xff)) : (k2 ? (v4 & 0xffff) : v4);
+      size = k1 ? 2u : (k2 ? 3u : 5u);
+      bad = avail < size;
     }
     if (bad) size = 64;
     uint32_t J = inb ? umin32(lane + size, 32) : 32;
@@ -1598,14 +1612,15 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
       uint32_t jn = __shfl_sync(kFull, J, (int)(J & 31));
       J = J < 32 ? jn : 32;
     }
-    bool is_tag = inb && ((R >> lane) & 1u);
-    uint32_t val = (is_tag && !bad) ? L : 0, incl = val;
+    const bool is_tag = inb && ((R >> lane) & 1u);
+    const uint32_t val = (is_tag && !bad) ? L : 0;
+    uint32_t incl = val;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       uint32_t u = __shfl_up_sync(kFull, incl, d);
       if (lane >= (uint32_t)d) incl += u;
     }
-    uint32_t my_op = op + (incl - val);
+    const uint32_t my_op = op + (incl - val);
     bool e = is_tag && bad;
     if (is_tag && !bad) {
       if (kind != 0 && (off == 0 || off > my_op)) e = true;    // :112-113
@@ -1613,21 +1628,27 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     }
     if (__any_sync(kFull, e)) return kInvalidInput;
 
-    bool go = is_tag;
-    bool dep = go && kind != 0 && (my_op - off + umin32(L, off) > op);
-    bool shrt = go && !dep && L <= 16;
+    // ---- copies.  An element is independent when its whole source lies before this step's
+    // output (literals always are); independent short elements are copied by their own lane with
+    // wide loads, long ones by the whole warp, dependent ones in order.
+    const bool indep = kind == 0 || (my_op - off + L <= op);
+    const bool shrt = is_tag && indep && L <= 16;
     if (shrt) {
+      const uint8_t* s = kind == 0 ? tags + pos + hdr : out + my_op - off;
+      const uint32_t sa = (uint32_t)((uintptr_t)s & 3), ssh = sa * 8;
+      const uint32_t* sw = (const uint32_t*)(s - sa);
+      const uint32_t nw = (L + sa + 3) >> 2;                     // 1..5 words hold the L source bytes
+      const uint32_t x0 = sw[0], x1 = nw > 1 ? sw[1] : 0u, x2 = nw > 2 ? sw[2] : 0u;
+      const uint32_t x3 = nw > 3 ? sw[3] : 0u, x4 = nw > 4 ? sw[4] : 0u;
+      const uint32_t b[4] = {__funnelshift_r(x0, x1, ssh), __funnelshift_r(x1, x2, ssh), __funnelshift_r(x2, x3, ssh),
+                             __funnelshift_r(x3, x4, ssh)};
       uint8_t* d = out + my_op;
-      if (kind == 0) {
-        const uint8_t* s = tags + pos + hdr;
-        for (uint32_t i = 0; i < L; i++) d[i] = s[i];
-      } else {
-        const uint8_t* s = out + my_op - off;  // off >= 1; byte-serial forward copy handles overlap
-        for (uint32_t i = 0; i < L; i++) d[i] = s[i];
-      }
+#pragma unroll
+      for (uint32_t i = 0; i < 16; i++)
+        if (i < L) d[i] = (uint8_t)(b[i >> 2] >> (8 * (i & 3)));
     }
-    uint32_t lmask = __ballot_sync(kFull, go && !dep && L > 16);
-    uint32_t dmask = __ballot_sync(kFull, dep);
+    uint32_t lmask = __ballot_sync(kFull, is_tag && indep && L > 16);
+    uint32_t dmask = __ballot_sync(kFull, is_tag && !indep);
     while (lmask) {
       int s = __ffs((int)lmask) - 1;
       lmask &= lmask - 1;
@@ -1635,11 +1656,7 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
       uint32_t sk = __shfl_sync(kFull, kind, s);
       uint32_t sx = __shfl_sync(kFull, kind == 0 ? pos + hdr : off, s);
       const uint8_t* srcp = sk == 0 ? tags + sx : out + so - sx;
-      if (sk == 0 || sx >= sl) {
-        warp_copy(out + so, srcp, sl, lane);
-      } else {
-        for (uint32_t i = lane; i < sl; i += 32) out[so + i] = srcp[i % sx];
-      }
+      warp_copy(out + so, srcp, sl, lane);
     }
     while (dmask) {
       __syncwarp();
