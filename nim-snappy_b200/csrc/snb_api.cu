@@ -8,6 +8,7 @@
 #include "../../include/snb.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -84,9 +85,9 @@ struct Ctx {
   float prof[6] = {0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
   uint32_t call_launches = 0;
-  int compress_warps = 0;    // 64 KiB blocks: encoder warps per SM with the table in shared memory
-  int compress_gwarps = 20;  // ... and with the table in global memory (L2 resident; leaves the SM its whole L1)
-  int compress_algo = 0;  // 0 auto, 1/2/4 warp encoders v1/v2/v3, 3 one thread per block
+  int compress_warps = 6;    // 64 KiB blocks: encoder warps per SM with the table in shared memory
+  int compress_gwarps = 18;  // ... and with the table in global memory (L2 resident; leaves the SM its whole L1)
+  int compress_algo = 0;  // 0 auto (= 5), 1/2/4/5 warp encoders v1/v2/v3/v5, 3 one thread per block
   int thread_min_chunks = 1 << 30;  // auto mode: batches at least this large use one thread per block (tables in HBM)
   std::string err;
 };
@@ -187,6 +188,7 @@ int do_init(int device) {
   CK(cudaSetDevice(device));
   g.device = device;
   CK(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, device));
+  if (const char* e = getenv("SNB_TUNE_SMS")) g.sms = std::max(1, atoi(e));   // tuning experiments only: persistent grids use this many SMs
   CK(cudaStreamCreateWithFlags(&g.s0, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&g.s_out, cudaStreamNonBlocking));
@@ -204,6 +206,7 @@ int do_init(int device) {
   CK(cudaMalloc((void**)&g.d_counters, kNumCounters * sizeof(uint32_t)));
   CK(cudaMalloc((void**)&g.d_total, 4 * sizeof(uint64_t)));
   CK(cudaFuncSetAttribute(snb::compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(snb::compress_kernel5, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   g.ready = true;
   return SNB_OK;
 }
@@ -231,28 +234,36 @@ void prof_collect(int first_pair, int n_pairs, int slot0) {
 
 // ---------------------------------------------------------------- launch geometry
 struct CompressGeom { uint32_t entries, warps, smem_warps, grid; size_t smem; };
+bool use_v5() { return g.compress_algo == 0 || g.compress_algo == 5; }
 CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
   CompressGeom cg;
   uint32_t e = 256;
   while (e < snb::kMaxTableEntries && e < max_len) e <<= 1;
   cg.entries = e;
-  size_t tbytes = (size_t)e * 2;
+  const size_t tbytes = (size_t)e * 2;
+  const bool v5 = use_v5();
+  const uint32_t max_warps = (v5 ? snb::kCompress5MaxThreads : snb::kCompressMaxThreads) / 32;
+  const size_t stage = v5 ? 0 : (size_t)snb::kStageWords * 4;   // per-warp staging area of the v3 encoder
   uint32_t ctas_per_sm;
   if (e == snb::kMaxTableEntries) {
     // 7 x 32 KiB tables fill the shared memory of an SM; further warps keep their table in L2
     cg.smem_warps = (uint32_t)std::max(0, std::min(7, g.compress_warps));
-    uint32_t extra = (uint32_t)std::max(0, std::min((int)(snb::kCompressMaxThreads / 32 - cg.smem_warps), g.compress_gwarps));
+    uint32_t extra = (uint32_t)std::max(0, std::min((int)(max_warps - cg.smem_warps), g.compress_gwarps));
     cg.warps = std::max(1u, cg.smem_warps + extra);
-    while (cg.smem_warps > 0 && cg.smem_warps * tbytes + cg.warps * snb::kStageWords * 4 > 227 * 1024) { cg.smem_warps--; cg.warps--; }
+    while (cg.smem_warps > 0 && cg.smem_warps * tbytes + cg.warps * stage > 227 * 1024) { cg.smem_warps--; cg.warps--; }
     ctas_per_sm = 1;
   } else {
     cg.warps = cg.smem_warps = 8;
-    ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (cg.warps * (tbytes + snb::kStageWords * 4) + 1024)));
+    ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (cg.warps * (tbytes + stage) + 1024)));
   }
-  cg.smem = cg.smem_warps * tbytes + cg.warps * snb::kStageWords * 4;  // tables, then the v3 encoder's staging area
+  cg.smem = cg.smem_warps * tbytes + cg.warps * stage;  // tables, then the staging area
   uint32_t need = (count + cg.warps - 1) / cg.warps;
   cg.grid = std::max(1u, std::min(need, (uint32_t)g.sms * ctas_per_sm));
   return cg;
+}
+void launch_compress(const snb::CompressArgs& a, const CompressGeom& cg, cudaStream_t st) {
+  if (use_v5()) SNB_LAUNCH(snb::compress_kernel5, cg.grid, cg.warps * 32, cg.smem, st, a);
+  else SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
 }
 
 // ---------------------------------------------------------------- device-side building blocks
@@ -318,7 +329,7 @@ int dev_compress_contig(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
       a.algo = (uint32_t)((g.compress_algo == 1 || g.compress_algo == 2) ? g.compress_algo : 4);
       a.defer_stored = mode == snb::kModeFrame ? 1u : 0u;
       if (p) prof_mark(2, st);
-      SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
+      launch_compress(a, cg, st);
     }
     count_launch();
     CK(cudaGetLastError());
@@ -831,7 +842,7 @@ int snb_dev_compress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const 
   a.algo = (uint32_t)((g.compress_algo == 1 || g.compress_algo == 2) ? g.compress_algo : 4);
   a.defer_stored = 0;
   prof_mark(2, st);
-  SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
+  launch_compress(a, cg, st);
   count_launch();
   CK(cudaGetLastError());
   prof_mark(3, st);

@@ -65,6 +65,17 @@ __device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gs
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 #endif
+// Cache hints (no destination register, no scoreboard): bring the line holding p towards the SM.
+#ifdef SNB_EMULATE
+__device__ __forceinline__ void prefetch_l1(const void*) {}
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+#endif
+#ifndef SNB_V5_HINT
+#define SNB_V5_HINT 1   // 0: none, 1: L1 hint, 2: L2 hint for the next window's candidates
+#endif
 // Unaligned little-endian 32-bit load built from aligned words.  Only words holding at least
 // one requested byte are touched.
 __device__ __forceinline__ uint32_t load32u(const uint8_t* p) {
@@ -1088,6 +1099,307 @@ __device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict_
 #undef SNB_FINISH
 }
 
+// --------------------------------------------------------------------- encodeBlock, v5
+// Window walk on ballot masks.  One pass handles the 32 positions [b, b+32) that hold the cursor:
+//
+//   resolve  lane l owns position b+l: 12 own bytes (one coalesced word per lane + shuffles, the next
+//            window's words prefetched), hash, table entry T, 12 candidate bytes, match length ml
+//            (0..12), the copy tag a 4..11-byte match would emit, and the match.any group of the hash.
+//   walk     as a chain arrival (post-copy lookup, encoder.nim:364-380) every lane knows its event --
+//            the first hit lane at or after itself (HB & lanes >= me) -- and so the next arrival
+//            J = event + ml.  The warp follows J from the entry arrival with one shuffle per arrival
+//            and collects the arrival mask A.
+//   masks    everything else is a function of A: looked-up lanes LK = union of [arrival, event],
+//            inserted lanes = LK | (A >> 1) (encoder.nim:371-377, :293-294), copy events = LK & hits,
+//            literal bytes = LK & ~events, literal starts = A & ~hits.  Output offsets are popcounts
+//            of those masks below the lane; every lane writes its own tag / literal byte.
+//   verify   a lookup is exact unless an earlier lane of its hash group was inserted in this window
+//            (then that lane is the true candidate): the arrivals before the first such lane are
+//            kept, the offending one is redone by a serial step straight on the table.  Matches that
+//            reach the 12-byte horizon end a batch and are measured with the whole warp.
+//   commit   the last inserted lane of each hash group writes the table.
+//
+// Chunk tails, strided literal runs (>= 32 probes, encoder.nim:311-331) and the rare conflicts take the
+// serial steps (one chain lookup, or 32 strided probes, straight on the table).
+__device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict__ in, uint32_t len,
+                                                      uint8_t* __restrict__ out, uint16_t* table,
+                                                      uint32_t abort_thr, uint32_t lane) {
+  InView v;
+  v.mis = (uint32_t)((uintptr_t)in & 3);
+  v.w = (const uint32_t*)(in - v.mis);
+  v.last = (len + v.mis - 1) >> 2;
+  if (len < kMinNonLiteral) return emit_literal_v2(out, v, 0, len, lane);
+
+  uint32_t tsize = 256;
+  while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
+  const uint32_t mask = tsize - 1;
+  {
+    uint32_t* t32 = (uint32_t*)table;
+    for (uint32_t i = lane; i < tsize / 2; i += 32) t32[i] = 0;
+  }
+  const uint32_t ip_limit = len - kInputMargin;
+  const uint32_t below = (1u << lane) - 1u;          // lanes before mine
+  const uint32_t notbelow = ~below;                  // my lane and the ones after it
+  const uint32_t own_q = (lane + v.mis) >> 2, own_s = ((lane + v.mis) & 3) * 8;
+  const uint32_t wlane = umin32(lane, 11u);          // 12 words hold a window's 44 bytes
+  uint32_t op = 0;
+  uint32_t ip = 0;          // chain mode: position of the pending post-copy lookup (<= ip_limit)
+  uint32_t next_emit = 0;   // literal mode: start of the pending literal
+  uint32_t pp = 1;          // literal mode: next probe position
+  uint32_t k = 0;           // literal mode: probes already done in this run
+  bool chain = false, force_slow = false;
+  bool m1_done = false;     // chain mode, ip on a window boundary: ip-1 has already been inserted
+  constexpr uint32_t kNoWindow = 0xffffffffu;
+  uint32_t Wn = 0, Wn_b = kNoWindow;   // prefetched own words of window Wn_b
+
+#define SNB_FINISH(from)                                                          \
+  do {                                                                            \
+    uint32_t f_ = (from);                                                         \
+    if (f_ < len) {                                                               \
+      uint32_t n_ = len - f_;                                                     \
+      if (op + literal_size(n_) > abort_thr) return kAborted;                     \
+      op += emit_literal_v2(out + op, v, f_, n_, lane);                           \
+    }                                                                             \
+    return op;                                                                    \
+  } while (0)
+
+  for (;;) {
+    __syncwarp();  // table writes (zeroing / previous commit / serial step) visible to every lane
+    const uint32_t b = (chain ? ip : pp) & ~31u;
+
+    if (force_slow || b + 32 >= ip_limit || (!chain && k >= 32)) {
+      force_slow = false;
+      m1_done = false;
+      if (chain) {
+        // ---- one serial chain step straight on the table (encoder.nim:364-380)
+        const uint32_t d1 = in_ld4(v, ip - 1), d = in_ld4(v, ip);
+        const uint32_t h1 = hash14(d1, mask), hh = hash14(d, mask);
+        const uint32_t tv = table[hh];
+        const uint32_t cand = (hh == h1) ? ip - 1 : tv;
+        __syncwarp();  // every lane has read before lane 0 writes
+        if (lane == 0) { table[h1] = (uint16_t)(ip - 1); table[hh] = (uint16_t)ip; }
+        const uint32_t m = common_prefix_v2(v, len, cand, ip, lane);
+        if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }   // :379-380
+        op += emit_copy_v2(out + op, ip - cand, m, lane);
+        ip += m;
+        if (op > abort_thr) return kAborted;
+        if (ip > ip_limit) SNB_FINISH(ip);
+        continue;
+      }
+      // ---- serial literal scan from (pp, k): 32 strided probes per step (encoder.nim:281-331)
+      uint32_t wip = pp, wskip = 32 + k;
+      uint32_t hit_ip = 0, hit_cand = 0;
+      bool found = false;
+      for (;;) {
+        uint32_t pos = wip, sk = wskip;
+        for (uint32_t j = 0; j < lane; j++) { uint32_t st = sk >> 5; sk += st; pos += st; }
+        uint32_t step = sk >> 5, sk_after = sk + step;
+        bool valid = (pos <= ip_limit) && (pos + step <= ip_limit);
+        uint32_t d = 0, h = 0x10000u + lane, tv = 0;
+        if (valid) { d = in_ld4(v, pos); h = hash14(d, mask); tv = table[h]; }
+        uint32_t grp = __match_any_sync(kFull, h);
+        uint32_t earlier = grp & below;
+        int src = earlier ? 31 - __clz((int)earlier) : (int)lane;
+        uint32_t pe = __shfl_sync(kFull, pos, src);
+        uint32_t c = earlier ? pe : tv;
+        bool hit = valid && (in_ld4(v, c) == d);
+        uint32_t hitmask = __ballot_sync(kFull, hit);
+        uint32_t vmask = __ballot_sync(kFull, valid);
+        if (hitmask) {
+          int kh = __ffs((int)hitmask) - 1;
+          uint32_t commit = (2u << kh) - 1u;
+          if (((commit >> lane) & 1u) && ((grp & commit) >> lane) == 1u) table[h] = (uint16_t)pos;
+          hit_ip = __shfl_sync(kFull, pos, kh);
+          hit_cand = __shfl_sync(kFull, c, kh);
+          found = true;
+          break;
+        }
+        if (vmask != kFull) break;
+        if ((grp >> lane) == 1u) table[h] = (uint16_t)pos;
+        wip = __shfl_sync(kFull, pos + step, 31);
+        wskip = __shfl_sync(kFull, sk_after, 31);
+        __syncwarp();
+      }
+      if (!found) SNB_FINISH(next_emit);
+      {
+        uint32_t n = hit_ip - next_emit;
+        if (op + literal_size(n) > abort_thr) return kAborted;
+        op += emit_literal_v2(out + op, v, next_emit, n, lane);
+      }
+      uint32_t m = 4 + common_prefix_v2(v, len, hit_cand + 4, hit_ip + 4, lane);
+      op += emit_copy_v2(out + op, hit_ip - hit_cand, m, lane);
+      ip = hit_ip + m;
+      if (op > abort_thr) return kAborted;
+      if (ip > ip_limit) SNB_FINISH(ip);
+      chain = true;
+      continue;
+    }
+
+    // ---- window [b, b+32): every lane is a valid lookup position (b + 32 < ip_limit)
+    const uint32_t p = b + lane;
+    if (chain && ip == b && !m1_done) {  // arrival on the window boundary after a serial step: ip-1 is not a lane here
+      const uint32_t d1 = in_ld4(v, ip - 1);
+      if (lane == 0) table[hash14(d1, mask)] = (uint16_t)(ip - 1);
+      __syncwarp();
+    }
+    m1_done = false;
+
+    // ---- resolve
+    const uint32_t W = (Wn_b == b) ? Wn : __ldg(v.w + (b >> 2) + wlane);
+    Wn = __ldg(v.w + umin32((b >> 2) + 8 + wlane, v.last));
+    Wn_b = b + 32;
+    const uint32_t w0 = __shfl_sync(kFull, W, (int)own_q), w1 = __shfl_sync(kFull, W, (int)own_q + 1);
+    const uint32_t w2 = __shfl_sync(kFull, W, (int)own_q + 2), w3 = __shfl_sync(kFull, W, (int)own_q + 3);
+    const uint32_t a0 = __funnelshift_r(w0, w1, own_s), a1 = __funnelshift_r(w1, w2, own_s), a2 = __funnelshift_r(w2, w3, own_s);
+    const uint32_t h = hash14(a0, mask);
+    const uint32_t T = table[h];
+    uint32_t ml;
+    {
+      uint32_t c0, c1, c2;
+      in_ld12u(v, T, c0, c1, c2);
+      const uint32_t x0 = a0 ^ c0, x1 = a1 ^ c1, x2 = a2 ^ c2;
+      const uint32_t xs = x0 ? x0 : (x1 ? x1 : x2);
+      const uint32_t base = x0 ? 0u : (x1 ? 4u : 8u);
+      ml = xs ? base + first_diff_byte(xs) : 12u;
+    }
+    const uint32_t off = p - T;
+    const bool c3 = off >= 2048;   // three-byte copy tag (ml <= 11 whenever the tag is used, encoder.nim:113-125)
+    const uint32_t tb = c3 ? ((((ml - 1) << 2) | 2u) | (off << 8))
+                           : ((((off >> 8) << 5) | ((ml - 4) << 2) | 1u) | ((off & 0xff) << 8));
+    const uint32_t grp = __match_any_sync(kFull, h);
+    const uint32_t eg = grp & below;                   // earlier lanes of my hash group
+    const uint32_t HB = __ballot_sync(kFull, ml >= 4);
+    const uint32_t C3 = __ballot_sync(kFull, c3);
+    // every lane as a chain arrival: its event lane, the looked-up lanes, the next arrival
+    const uint32_t qb = HB & notbelow;
+    const uint32_t evt = qb ? (uint32_t)__ffs((int)qb) - 1u : 32u;
+    const uint32_t eml = __shfl_sync(kFull, ml, (int)(evt & 31u));
+    // J < 32: next arrival in this window; 32..63: beyond it; 64 + e: the match at lane e reaches the horizon;
+    // 128: no hit up to the window end (the literal run goes on)
+    const uint32_t J = evt >= 32 ? 128u : (eml >= 12 ? 64u + evt : evt + eml);
+    const uint32_t lkmask = notbelow & ((2u << umin32(evt, 31u)) - 1u);
+#if SNB_V5_HINT
+    // hint for the next window: its (pre-commit) table entries say where its candidates most likely are
+    uint32_t Tn;
+    {
+      const uint32_t n0 = __shfl_sync(kFull, Wn, (int)own_q), n1 = __shfl_sync(kFull, Wn, (int)own_q + 1);
+      Tn = table[hash14(__funnelshift_r(n0, n1, own_s), mask)];
+    }
+#endif
+
+    uint32_t ins = 0;      // lanes inserted in this pass
+    uint32_t c = 0;        // entry arrival lane
+    uint32_t noprev = 0;   // arrival whose predecessor lane is not inserted again (a probe hit)
+    if (!chain) {
+      // ---- the literal run entering the window: stride-1 probes at lanes [l0, bend)
+      const uint32_t l0 = pp - b;
+      const uint32_t bend = umin32(32u, l0 + (32u - k));
+      const uint32_t range = (0xffffffffu << l0) & (bend >= 32 ? 0xffffffffu : ((1u << bend) - 1u));
+      const uint32_t qh = HB & range;
+      const uint32_t q0 = qh ? (uint32_t)__ffs((int)qh) - 1u : 32u;
+      const uint32_t run = range & (q0 >= 32 ? 0xffffffffu : ((2u << q0) - 1u));   // probes performed
+      const uint32_t stale = __ballot_sync(kFull, (eg & run) != 0) & run;
+      if (stale) { force_slow = true; continue; }
+      if (q0 >= 32) {  // every probe missed: insert them and move on (k == 32 switches to the strided scan)
+        if (((run >> lane) & 1u) && ((grp & run) >> lane) == 1u) table[h] = (uint16_t)p;
+        k += (uint32_t)__popc(run);
+        pp = b + bend;
+        continue;
+      }
+      {  // :336-338; the copy at q0 is the first event of the walk
+        const uint32_t n = b + q0 - next_emit;
+        if (op + literal_size(n) > abort_thr) return kAborted;
+        op += emit_literal_v2(out + op, v, next_emit, n, lane);
+      }
+      ins = run;
+      chain = true;
+      c = q0;
+      noprev = 1u << q0;
+    } else {
+      c = ip - b;
+    }
+
+    bool done = false;  // block finished inside this pass (ip > ip_limit after a copy)
+    for (;;) {          // one batch per turn; a match that reaches the horizon ends a batch
+      uint32_t A = 0, cc = c;
+      do { A |= 1u << cc; cc = __shfl_sync(kFull, J, (int)cc); } while (cc < 32);
+      bool onp = (A >> lane) & 1u;
+      uint32_t LK = __reduce_or_sync(kFull, onp ? lkmask : 0u);
+      uint32_t insb = LK | ((A & ~noprev) >> 1);
+      const uint32_t stale = __ballot_sync(kFull, ((LK >> lane) & 1u) && (eg & (ins | insb)) != 0);
+      uint32_t slow_at = 32;
+      if (stale) {  // keep the arrivals whose lookups all precede the first stale lane
+        const uint32_t xs = (uint32_t)__ffs((int)stale) - 1u;
+        slow_at = 31u - (uint32_t)__clz((int)(A & ((2u << xs) - 1u)));
+        A &= (1u << slow_at) - 1u;
+        onp = (A >> lane) & 1u;
+        LK = __reduce_or_sync(kFull, onp ? lkmask : 0u);
+        insb = LK | ((A & ~noprev) >> 1);
+        cc = 32;
+      }
+      ins |= insb;
+      noprev = 0;
+      const uint32_t Ev = LK & HB;
+      uint32_t EvT = Ev, tail = 0;
+      if (cc >= 64 && cc < 96) EvT &= ~(1u << (cc - 64));                        // its copy is emitted below
+      if (cc == 128) tail = 0xffffffffu << (31u - (uint32_t)__clz((int)A));      // the last run leaves the window
+      const uint32_t LitB = LK & ~Ev & ~tail;    // literal bytes
+      const uint32_t LS = A & ~HB & ~tail;       // literal starts (one tag byte each: n <= 31)
+      const uint32_t E3 = EvT & C3;
+      {
+        const uint32_t offl = (uint32_t)(__popc(LitB & below) + __popc(LS & below) + 2 * __popc(EvT & below) + __popc(E3 & below));
+        uint8_t* o = out + op + offl;
+        if ((LS >> lane) & 1u) { o[0] = (uint8_t)((evt - lane - 1u) << 2); o += 1; }
+        if ((LitB >> lane) & 1u) o[0] = (uint8_t)a0;
+        if ((EvT >> lane) & 1u) {
+          o[0] = (uint8_t)tb; o[1] = (uint8_t)(tb >> 8);
+          if (c3) o[2] = (uint8_t)(tb >> 16);
+        }
+      }
+      op += (uint32_t)(__popc(LitB) + __popc(LS) + 2 * __popc(EvT) + __popc(E3));
+      if (op > abort_thr) return kAborted;
+      if (slow_at < 32) { ip = b + slow_at; force_slow = true; break; }
+      if (cc < 64) { ip = b + cc; break; }
+      if (cc == 128) {
+        const uint32_t cl = 31u - (uint32_t)__clz((int)A);
+        chain = false; next_emit = b + cl; pp = b + 32; k = 31 - cl;
+        break;
+      }
+      // ---- the copy at lane e is at least 12 bytes long: measured with the whole warp (encoder.nim:130-182)
+      const uint32_t e = cc - 64;
+      const uint32_t cand = __shfl_sync(kFull, T, (int)e);
+      const uint32_t m = 12 + common_prefix_v2(v, len, cand + 12, b + e + 12, lane);
+      op += emit_copy_v2(out + op, b + e - cand, m, lane);
+      ip = b + e + m;
+      if (op > abort_thr) return kAborted;
+      if (ip > ip_limit) { done = true; break; }
+      c = ip - b;
+      if (c >= 32) break;
+    }
+    if (chain && !force_slow && ip > ip_limit) done = true;   // encoder.nim:362-363
+    // the next arrival's ip-1 insert when no window pass will own it (lane c-1 of the arrival rule)
+    bool pend_insert = false;
+    if (chain && !force_slow && !done && (ip & 31u) == 0) {
+      if (ip == b + 32) ins |= 1u << 31; else pend_insert = true;
+      m1_done = true;
+    }
+#if SNB_V5_HINT == 1
+    prefetch_l1(v.w + ((Tn + v.mis) >> 2));
+#elif SNB_V5_HINT == 2
+    prefetch_l2(v.w + ((Tn + v.mis) >> 2));
+#endif
+    // ---- commit: the last inserted lane of each hash group writes the table
+    if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[h] = (uint16_t)p;
+    if (done) SNB_FINISH(ip);
+    if (pend_insert) {
+      __syncwarp();
+      const uint32_t d1 = in_ld4(v, ip - 1);
+      if (lane == 0) table[hash14(d1, mask)] = (uint16_t)(ip - 1);
+    }
+  }
+#undef SNB_FINISH
+}
+
 struct CompressArgs {
   const uint8_t* in_base;
   uint8_t* out_base;
@@ -1118,16 +1430,20 @@ __device__ __forceinline__ uint32_t varint32_len(uint32_t v) {
   return v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5;
 }
 
+template <int kAlgo>
 __device__ __forceinline__ uint32_t encode_block(uint32_t algo, const uint8_t* in, uint32_t len, uint8_t* out,
                                                  uint16_t* table, uint32_t abort_thr, uint32_t lane, uint32_t stage,
                                                  bool tglobal) {
+  if (kAlgo == 5) return compress_block_v5(in, len, out, table, abort_thr, lane);
   if (algo == 1) return compress_block_warp(in, len, out, table, abort_thr, lane);
   if (algo == 2) return compress_block_v2(in, len, out, table, abort_thr, lane);
+  if (algo == 5) return compress_block_v5(in, len, out, table, abort_thr, lane);
   return compress_block_v3(in, len, out, table, abort_thr, lane, stage, tglobal);
 }
 
 // One job = one encodeFrame (encoder.nim:385-426), one bare encodeBlock, or one whole
 // single-block `compress` message (snappy.nim:27-64).
+template <int kAlgo>
 __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job, uint16_t* table, uint32_t lane,
                                              uint32_t stage, bool tglobal) {
   uint64_t ioff = a.in_off ? a.in_off[job] : (uint64_t)job * kMaxBlock;
@@ -1141,7 +1457,7 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
   const uint32_t pre = frame ? 8u + hl : hl;
   const uint32_t thr = frame ? len - len / 8 : kNoAbort;
   uint32_t bl = frame ? kAborted : 0u;
-  if (frame ? len >= kMinNonLiteral : len > 0) bl = encode_block(a.algo, in, len, out + pre, table, thr, lane, stage, tglobal);  // encoder.nim:401-406
+  if (frame ? len >= kMinNonLiteral : len > 0) bl = encode_block<kAlgo>(a.algo, in, len, out + pre, table, thr, lane, stage, tglobal);  // encoder.nim:401-406
   uint32_t total;
   if (frame) {
     uint32_t crc = a.crc[job];
@@ -1190,7 +1506,29 @@ __global__ void __launch_bounds__(kCompressMaxThreads, 1) compress_kernel(Compre
     if (lane == 0) job = atomicAdd(a.counter, 1u);
     job = __shfl_sync(kFull, job, 0);
     if (job >= a.count) return;
-    compress_job(a, job, table, lane, stage, tglobal);
+    compress_job<0>(a, job, table, lane, stage, tglobal);
+    __syncwarp();
+  }
+}
+
+// The v5 encoder on its own register budget (no staging area: the tables are the only shared memory).
+#ifndef SNB_COMPRESS5_MAXT
+#define SNB_COMPRESS5_MAXT 768
+#endif
+constexpr uint32_t kCompress5MaxThreads = SNB_COMPRESS5_MAXT;
+__global__ void __launch_bounds__(kCompress5MaxThreads, 1) compress_kernel5(CompressArgs a) {
+  SNB_DYN_SMEM(smem);
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool tglobal = warp >= a.smem_warps;
+  uint16_t* table = !tglobal
+                        ? (uint16_t*)smem + (size_t)warp * a.table_entries
+                        : a.gtables + ((size_t)blockIdx.x * (blockDim.x / 32 - a.smem_warps) + (warp - a.smem_warps)) * a.table_entries;
+  for (;;) {
+    uint32_t job = 0;
+    if (lane == 0) job = atomicAdd(a.counter, 1u);
+    job = __shfl_sync(kFull, job, 0);
+    if (job >= a.count) return;
+    compress_job<5>(a, job, table, lane, 0, tglobal);
     __syncwarp();
   }
 }

@@ -82,7 +82,7 @@ def test_decoder_differential_fuzz(emu_api, oracle):
         P.check_framed_decode_parity(emu_api, oracle, s, 4096)
 
 
-@pytest.mark.parametrize("algo", [1, 2, 3, 4])
+@pytest.mark.parametrize("algo", [1, 2, 3, 4, 5])
 def test_every_block_encoder_variant(emu_api, oracle, algo):
     """The three block encoders (per-step warp, window-resolve warp, thread-per-block with the table in
     global memory) are byte-identical; the auto mode picks between the last two by batch size."""
