@@ -1901,16 +1901,49 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
   const uint32_t tmis = (uint32_t)((uintptr_t)tags & 3);
   const uint32_t* const tw = (const uint32_t*)(tags - tmis);
   const uint32_t tw_last = (tn + tmis - 1) >> 2;   // tn >= 1 here
+  // 256 stream bytes held in registers: lane l has words kb + l (Wa) and kb + 32 + l (Wb); Wb is fetched
+  // long before the cursor reaches it, so a step never waits for the stream
+  uint32_t kb = 0;
+  uint32_t Wa = __ldg(tw + umin32(lane, tw_last)), Wb = __ldg(tw + umin32(32 + lane, tw_last));
+  // short elements (<= 16 bytes) of the previous step: sources already loaded, stores still to do.  They are
+  // flushed after the next step's tag parse, so the source loads never stall the warp.
+  uint32_t pL = 0, pdst = 0, pssh = 0, px0 = 0, px1 = 0, px2 = 0, px3 = 0, px4 = 0;
+
+#define SNB_FLUSH_SHORT()                                                                         \
+  do {                                                                                            \
+    if (pL) {                                                                                     \
+      const uint32_t b_[4] = {__funnelshift_r(px0, px1, pssh), __funnelshift_r(px1, px2, pssh),   \
+                              __funnelshift_r(px2, px3, pssh), __funnelshift_r(px3, px4, pssh)};  \
+      uint8_t* d_ = out + pdst;                                                                   \
+      _Pragma("unroll") for (uint32_t i_ = 0; i_ < 8; i_++)                                       \
+        if (i_ < pL) d_[i_] = (uint8_t)(b_[i_ >> 2] >> (8 * (i_ & 3)));                           \
+      if (pL > 8) {                                                                               \
+        _Pragma("unroll") for (uint32_t i_ = 8; i_ < 16; i_++)                                    \
+          if (i_ < pL) d_[i_] = (uint8_t)(b_[i_ >> 2] >> (8 * (i_ & 3)));                         \
+      }                                                                                           \
+      pL = 0;                                                                                     \
+    }                                                                                             \
+  } while (0)
 
   while (ip < tn) {
-    __syncwarp();  // output bytes of the previous step are visible to every lane
-    // ---- the 36 stream bytes of this step: one aligned word per lane (0..10), then every lane
-    // assembles the 8 bytes starting at its own position through shuffles
+    // ---- the 36 stream bytes of this step, assembled from the register window through shuffles
     const uint32_t i0 = ip + tmis;
-    const uint32_t W = __ldg(tw + umin32((i0 >> 2) + lane, tw_last));   // lanes >= 11 load a word nobody uses
-    const uint32_t q = ((i0 & 3) + lane) >> 2, sh = (((i0 & 3) + lane) & 3) * 8;
-    const uint32_t w0 = __shfl_sync(kFull, W, (int)q), w1 = __shfl_sync(kFull, W, (int)q + 1);
-    const uint32_t w2 = __shfl_sync(kFull, W, (int)q + 2);
+    {
+      const uint32_t k0 = i0 >> 2;
+      if (k0 - kb >= 32) {
+        if (k0 - kb < 64) { Wa = Wb; kb += 32; }
+        else { kb = k0; Wa = __ldg(tw + umin32(kb + lane, tw_last)); }
+        Wb = __ldg(tw + umin32(kb + 32 + lane, tw_last));
+      }
+    }
+    const uint32_t j = ((i0 >> 2) - kb) + (((i0 & 3) + lane) >> 2), sh = (((i0 & 3) + lane) & 3) * 8;
+    uint32_t w0, w1, w2;
+    {
+      const uint32_t a0 = __shfl_sync(kFull, Wa, (int)j), b0 = __shfl_sync(kFull, Wb, (int)j);
+      const uint32_t a1 = __shfl_sync(kFull, Wa, (int)j + 1), b1 = __shfl_sync(kFull, Wb, (int)j + 1);
+      const uint32_t a2 = __shfl_sync(kFull, Wa, (int)j + 2), b2 = __shfl_sync(kFull, Wb, (int)j + 2);
+      w0 = j < 32 ? a0 : b0; w1 = j + 1 < 32 ? a1 : b1; w2 = j + 2 < 32 ? a2 : b2;
+    }
     const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
     const uint32_t pos = ip + lane;
     const bool inb = pos < tn;
@@ -1966,24 +1999,22 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     }
     if (__any_sync(kFull, e)) return kInvalidInput;
 
+    // ---- the previous step's short elements reach memory now; after the barrier every byte before `op` is visible
+    SNB_FLUSH_SHORT();
+    __syncwarp();
+
     // ---- copies.  An element is independent when its whole source lies before this step's
     // output (literals always are); independent short elements are copied by their own lane with
-    // wide loads, long ones by the whole warp, dependent ones in order.
+    // wide loads (stored one step later), long ones by the whole warp, dependent ones in order.
     const bool indep = kind == 0 || (my_op - off + L <= op);
-    const bool shrt = is_tag && indep && L <= 16;
-    if (shrt) {
+    if (is_tag && indep && L <= 16) {
       const uint8_t* s = kind == 0 ? tags + pos + hdr : out + my_op - off;
-      const uint32_t sa = (uint32_t)((uintptr_t)s & 3), ssh = sa * 8;
+      const uint32_t sa = (uint32_t)((uintptr_t)s & 3);
       const uint32_t* sw = (const uint32_t*)(s - sa);
       const uint32_t nw = (L + sa + 3) >> 2;                     // 1..5 words hold the L source bytes
-      const uint32_t x0 = sw[0], x1 = nw > 1 ? sw[1] : 0u, x2 = nw > 2 ? sw[2] : 0u;
-      const uint32_t x3 = nw > 3 ? sw[3] : 0u, x4 = nw > 4 ? sw[4] : 0u;
-      const uint32_t b[4] = {__funnelshift_r(x0, x1, ssh), __funnelshift_r(x1, x2, ssh), __funnelshift_r(x2, x3, ssh),
-                             __funnelshift_r(x3, x4, ssh)};
-      uint8_t* d = out + my_op;
-#pragma unroll
-      for (uint32_t i = 0; i < 16; i++)
-        if (i < L) d[i] = (uint8_t)(b[i >> 2] >> (8 * (i & 3)));
+      px0 = sw[0]; px1 = nw > 1 ? sw[1] : 0u; px2 = nw > 2 ? sw[2] : 0u;
+      px3 = nw > 3 ? sw[3] : 0u; px4 = nw > 4 ? sw[4] : 0u;
+      pssh = sa * 8; pL = L; pdst = my_op;
     }
     uint32_t lmask = __ballot_sync(kFull, is_tag && indep && L > 16);
     uint32_t dmask = __ballot_sync(kFull, is_tag && !indep);
@@ -1996,20 +2027,26 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
       const uint8_t* srcp = sk == 0 ? tags + sx : out + so - sx;
       warp_copy(out + so, srcp, sl, lane);
     }
-    while (dmask) {
-      __syncwarp();
-      int s = __ffs((int)dmask) - 1;
-      dmask &= dmask - 1;
-      uint32_t so = __shfl_sync(kFull, my_op, s), sl = __shfl_sync(kFull, L, s), sx = __shfl_sync(kFull, off, s);
-      const uint8_t* srcp = out + so - sx;
-      if (sx >= sl) { for (uint32_t i = lane; i < sl; i += 32) out[so + i] = srcp[i]; }
-      else { for (uint32_t i = lane; i < sl; i += 32) out[so + i] = srcp[i % sx]; }
+    if (dmask) {  // a source inside this step's output: everything before it has to be in memory first
+      SNB_FLUSH_SHORT();
+      while (dmask) {
+        __syncwarp();
+        int s = __ffs((int)dmask) - 1;
+        dmask &= dmask - 1;
+        uint32_t so = __shfl_sync(kFull, my_op, s), sl = __shfl_sync(kFull, L, s), sx = __shfl_sync(kFull, off, s);
+        const uint8_t* srcp = out + so - sx;
+        if (sx >= sl) { for (uint32_t i = lane; i < sl; i += 32) out[so + i] = srcp[i]; }
+        else { for (uint32_t i = lane; i < sl; i += 32) out[so + i] = srcp[i % sx]; }
+      }
     }
     uint32_t tagmask = __ballot_sync(kFull, is_tag);
     int last = 31 - __clz((int)tagmask);
     ip = __shfl_sync(kFull, pos + size, last);
     op += __shfl_sync(kFull, incl, 31);
   }
+  SNB_FLUSH_SHORT();
+#undef SNB_FLUSH_SHORT
+  __syncwarp();
   if (op != ulen) return kInvalidInput;                        // snappy.nim:107-108
   *written = op;
   return kOk;
@@ -2026,7 +2063,10 @@ struct DecompressArgs {
   uint32_t verify;     // 1: compare masked CRC of the produced bytes with chunk.crc
 };
 
-__global__ void __launch_bounds__(256) decompress_kernel(DecompressArgs a, const CrcTables* g) {
+#ifndef SNB_DEC_MINB
+#define SNB_DEC_MINB 4
+#endif
+__global__ void __launch_bounds__(256, SNB_DEC_MINB) decompress_kernel(DecompressArgs a, const CrcTables* g) {
   __shared__ CrcSmem t;
   if (a.verify) crc_stage_tables(&t, g);
   uint32_t lane = threadIdx.x & 31;
