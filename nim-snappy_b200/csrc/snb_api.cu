@@ -34,6 +34,8 @@ constexpr uint64_t kFrameStride = 65664;           // >= 65544 (stored frame) an
 constexpr uint64_t kRawStride = 76544;             // >= maxCompressedLen(65536) = 76490, multiple of 128
 constexpr uint32_t kDevSlabChunks = 16384;         // 1 GiB of input per device-side slab
 constexpr uint32_t kHostSlabChunks = 4096;         // 256 MiB of input per host<->device slab (fills 148 SMs x 20 encoder warps)
+constexpr uint32_t kGroupShift = 9;                // streaming pipeline: 512 chunks (32 MiB of input) per H2D piece / D2H group
+constexpr uint32_t kGroupChunks = 1u << kGroupShift;
 constexpr int kNumCounters = 256;
 const uint8_t kStreamHeader[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};  // codec.nim:33-34
 
@@ -79,14 +81,18 @@ struct Ctx {
   uint64_t* d_total = nullptr;  // 4 device scalars
   DevBuf scratch, lens, offs, crcs, chunks, status, outlen, tables, in[2], out[2];
   PinBuf h_in[2], h_out[2], h_meta[2];
+  DevBuf group_done, group_end;     // streaming compress: per-group placement counters / end offsets
+  PinBuf h_flags[2], h_arr;         // host-mapped group-complete flags per slab parity; arrival values per piece
+  uint32_t* d_arrived = nullptr;    // chunks whose input has landed (streaming compress), then a timeout flag
+  cudaEvent_t ev_reset = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   cudaEvent_t ev_prof[12] = {};
   bool profiling = false;
   float prof[6] = {0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
   uint32_t call_launches = 0;
-  int compress_warps = 6;    // 64 KiB blocks: encoder warps per SM with the table in shared memory
-  int compress_gwarps = 18;  // ... and with the table in global memory (L2 resident; leaves the SM its whole L1)
+  int compress_warps = 4;    // 64 KiB blocks: encoder warps per SM with the table in shared memory (more would squeeze the L1 below what the candidate loads need)
+  int compress_gwarps = 20;  // ... and with the table in global memory (L2)
   int compress_algo = 0;  // 0 auto (= 5), 1/2/4/5 warp encoders v1/v2/v3/v5, 3 one thread per block
   int thread_min_chunks = 1 << 30;  // auto mode: batches at least this large use one thread per block (tables in HBM)
   std::string err;
@@ -205,6 +211,10 @@ int do_init(int device) {
   CK(cudaMemcpy(g.d_hdr, kStreamHeader, 10, cudaMemcpyHostToDevice));
   CK(cudaMalloc((void**)&g.d_counters, kNumCounters * sizeof(uint32_t)));
   CK(cudaMalloc((void**)&g.d_total, 4 * sizeof(uint64_t)));
+  CK(cudaMalloc((void**)&g.d_arrived, 4 * sizeof(uint32_t)));
+  CK(cudaMemset(g.d_arrived, 0, 4 * sizeof(uint32_t)));
+  CK(cudaEventCreateWithFlags(&g.ev_reset, cudaEventDisableTiming));
+  CK(cudaFuncSetAttribute(snb::compress_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(snb::compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(snb::compress_kernel5, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   g.ready = true;
@@ -352,6 +362,64 @@ int dev_compress_contig(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
   return SNB_OK;
 }
 
+// The same job as dev_compress_contig in ONE persistent kernel per slab (compress_stream_kernel: CRC, encode,
+// in-order packing).  d_arrived (optional) lets the kernel start while the input is still being copied in;
+// h_flags (optional, host-mapped, one word per group of kGroupChunks chunks over the whole call) receives
+// each group's end offset + 1 as soon as the group is packed.  chunk0: index of d_in's first chunk in
+// d_arrived's units.  d_total[0] receives the end offset.
+int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t* d_dst, uint64_t dst_base,
+                        uint32_t* d_frame_lens, cudaStream_t st, const uint32_t* d_arrived, uint64_t chunk0,
+                        unsigned long long* h_flags) {
+  uint64_t count64 = (n + kChunk - 1) / kChunk;
+  if (count64 == 0) {
+    CK(cudaMemcpyAsync(g.d_total, &dst_base, 8, cudaMemcpyHostToDevice, st));
+    return SNB_OK;
+  }
+  const uint32_t slab = (uint32_t)std::min<uint64_t>(count64, kDevSlabChunks);
+  const uint64_t kSlotStride = mode == snb::kModeFrame ? kFrameStride : kRawStride;
+  CompressGeom cg = compress_geom((uint32_t)kChunk, slab);
+  // the CRC tables share the dynamic shared memory with the hash tables
+  while (cg.smem_warps > 0 && cg.smem_warps * (size_t)cg.entries * 2 + sizeof(snb::CrcSmem) > 227 * 1024) cg.smem_warps--;
+  cg.smem = cg.smem_warps * (size_t)cg.entries * 2 + sizeof(snb::CrcSmem);
+  CK(g.scratch.ensure((size_t)slab * kSlotStride + 4096));
+  CK(g.lens.ensure((size_t)slab * 4));
+  CK(g.group_done.ensure(((size_t)slab / kGroupChunks + 2) * 4));
+  CK(g.group_end.ensure(((size_t)slab / kGroupChunks + 2) * 8));
+  CK(g.tables.ensure((size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2 + 256));
+  unsigned long long* d_total = (unsigned long long*)g.d_total;
+  for (uint64_t first = 0; first < count64; first += slab) {
+    const uint32_t cnt = (uint32_t)std::min<uint64_t>(slab, count64 - first);
+    const uint8_t* sin = d_in + first * kChunk;
+    const uint64_t slen = std::min<uint64_t>(n - first * kChunk, (uint64_t)cnt * kChunk);
+    const bool p = g.profiling && first == 0;
+    CK(cudaMemsetAsync(g.lens.p, 0, (size_t)cnt * 4, st));
+    CK(cudaMemsetAsync(g.group_done.p, 0, ((size_t)cnt / kGroupChunks + 1) * 4, st));
+    SNB_LAUNCH(snb::stream_init_kernel, 1, 32, 0, st, d_total + 1, first == 0 ? (const unsigned long long*)nullptr : d_total,
+               (unsigned long long)dst_base, d_total);
+    count_launch();
+    snb::StreamArgs a;
+    a.c.in_base = sin; a.c.out_base = g.scratch.as<uint8_t>(); a.c.in_off = nullptr; a.c.in_len = nullptr; a.c.out_off = nullptr;
+    a.c.total_len = slen; a.c.out_stride = kSlotStride; a.c.crc = nullptr; a.c.out_len = g.lens.as<uint32_t>();
+    a.c.count = cnt; a.c.mode = mode;
+    CKS(next_counter(st, &a.c.counter));
+    a.c.table_entries = cg.entries; a.c.smem_warps = cg.smem_warps; a.c.gtables = g.tables.as<uint16_t>();
+    a.c.algo = 5; a.c.defer_stored = mode == snb::kModeFrame ? 1u : 0u;
+    a.dst = d_dst; a.frontier = d_total + 1; a.arrived = d_arrived;
+    a.group_done = g.group_done.as<uint32_t>(); a.group_end = g.group_end.as<unsigned long long>();
+    a.host_flags = h_flags ? h_flags + first / kGroupChunks : nullptr;
+    a.total = d_total; a.error = g.d_arrived + 1; a.crc_tables = g.d_tables;
+    a.group_shift = kGroupShift; a.chunk0 = (uint32_t)(chunk0 + first);
+    if (p) prof_mark(2, st);
+    SNB_LAUNCH(snb::compress_stream_kernel, std::min(cg.grid, (uint32_t)g.sms), cg.warps * 32, cg.smem, st, a);
+    count_launch();
+    CK(cudaGetLastError());
+    if (p) prof_mark(3, st);
+    if (d_frame_lens)
+      CK(cudaMemcpyAsync(d_frame_lens + first, g.lens.p, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return SNB_OK;
+}
+
 int launch_decompress(const uint8_t* d_in, uint8_t* d_out, const snb::Chunk* d_chunks, uint32_t count, int verify,
                       int32_t* d_status, uint32_t* d_outlen, cudaStream_t st) {
   if (!count) return SNB_OK;
@@ -376,64 +444,136 @@ bool is_pinned(const void* p) {
 }
 
 // ---------------------------------------------------------------- host-buffer compress pipeline
-// Streams `n` input bytes through the GPU in slabs: H2D (s_in) | kernels (s0) | D2H (s_out),
-// double buffered.  The packed output of slab k lands at out + *pos.
+// Streams `n` input bytes through the GPU: the input goes host -> device in 32 MiB pieces (s_in), ONE
+// persistent kernel per <= 1 GiB slab (s0) starts on the first piece and chases the copy, and every packed
+// group of 512 chunks goes device -> host (s_out) as soon as the kernel flags it -- H2D, kernel and D2H of the
+// same slab overlap, and so do neighbouring slabs (double-buffered device buffers).  Pinned caller buffers
+// are DMA'd directly; pageable ones go through the driver's staging.
+int wait_group_flag(volatile unsigned long long* flag, cudaEvent_t kernel_done, unsigned long long* end) {
+  for (uint64_t spins = 0;; spins++) {
+    unsigned long long v = *flag;
+    if (v) { *end = v - 1; return SNB_OK; }
+    if ((spins & 1023) == 1023) {
+      cudaError_t q = cudaEventQuery(kernel_done);
+      if (q == cudaSuccess) {  // kernel finished: the flag must be there
+        v = *flag;
+        if (v) { *end = v - 1; return SNB_OK; }
+        g.err = "streaming compress: kernel finished without completing a group";
+        return SNB_CUDA_ERROR;
+      }
+      if (q != cudaErrorNotReady) return fail("cudaEventQuery(compress kernel)", q);
+    }
+#if !defined(SNB_EMULATE) && (defined(__x86_64__) || defined(__i386__))
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
 int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, uint32_t mode) {
   if (n == 0) return SNB_OK;
-  const uint64_t slab_bytes = (uint64_t)kHostSlabChunks * kChunk;
-  const uint64_t nslab = (n + slab_bytes - 1) / slab_bytes;
-  const size_t per_block = mode == snb::kModeFrame ? (size_t)(kChunk + 8) : (size_t)SNB_MAX_COMPRESSED_FRAME_LEN;
-  const size_t out_slab_cap = (size_t)kHostSlabChunks * per_block + 65536;
-  const bool pin_in = is_pinned(in), pin_out = is_pinned(out);
-  const size_t in_cap = (size_t)std::min<uint64_t>(n, slab_bytes);
-  const int nbuf = nslab > 1 ? 2 : 1;
-  for (int i = 0; i < nbuf; i++) {
-    CK(g.in[i].ensure(in_cap + 64));
-    CK(g.out[i].ensure(nslab > 1 ? out_slab_cap : (size_t)((n + kChunk - 1) / kChunk) * per_block + 65536));
-    if (!pin_in) CK(g.h_in[i].ensure(in_cap));
-    if (!pin_out) CK(g.h_out[i].ensure(g.out[i].cap));
-    CK(g.h_meta[i].ensure(64));
-  }
-  uint64_t slab_len[2] = {0, 0};
-  auto finish = [&](uint64_t k) -> int {
-    int s = (int)(k & 1);
-    CK(cudaEventSynchronize(g.ev_comp[s]));
-    uint64_t total = *g.h_meta[s].as<uint64_t>();
-    if (pin_out) {
-      CK(cudaMemcpyAsync(out + *pos, g.out[s].p, total, cudaMemcpyDeviceToHost, g.s_out));
-      CK(cudaEventRecord(g.ev_d2h[s], g.s_out));
-    } else {
-      CK(cudaMemcpyAsync(g.h_out[s].p, g.out[s].p, total, cudaMemcpyDeviceToHost, g.s_out));
-      CK(cudaStreamSynchronize(g.s_out));
-      memcpy(out + *pos, g.h_out[s].p, total);
-      CK(cudaEventRecord(g.ev_d2h[s], g.s_out));
-    }
+  if (!use_v5()) {  // the older encoders keep the plain slab pipeline
+    const uint64_t count = (n + kChunk - 1) / kChunk;
+    const size_t per_block = mode == snb::kModeFrame ? (size_t)(kChunk + 8) : (size_t)SNB_MAX_COMPRESSED_FRAME_LEN;
+    CK(g.in[0].ensure(n + 64));
+    CK(g.out[0].ensure(count * per_block + 65536));
+    CK(g.h_meta[0].ensure(64));
+    CK(cudaMemcpyAsync(g.in[0].p, in, n, cudaMemcpyHostToDevice, g.s0));
+    CKS(dev_compress_contig(g.in[0].as<uint8_t>(), n, mode, g.out[0].as<uint8_t>(), 0, nullptr, g.s0));
+    CK(cudaMemcpyAsync(g.h_meta[0].p, g.d_total, 8, cudaMemcpyDeviceToHost, g.s0));
+    CK(cudaStreamSynchronize(g.s0));
+    const uint64_t total = *g.h_meta[0].as<uint64_t>();
+    CK(cudaMemcpy(out + *pos, g.out[0].p, total, cudaMemcpyDeviceToHost));
     *pos += total;
     return SNB_OK;
-  };
-  for (uint64_t k = 0; k < nslab; k++) {
-    int s = (int)(k & 1);
-    uint64_t off = k * slab_bytes, len = std::min<uint64_t>(slab_bytes, n - off);
-    slab_len[s] = len;
-    if (k >= 2) CK(cudaStreamWaitEvent(g.s_in, g.ev_comp[s], 0));  // d_in[s] consumed by slab k-2
-    if (pin_in) {
-      CK(cudaMemcpyAsync(g.in[s].p, in + off, len, cudaMemcpyHostToDevice, g.s_in));
-    } else {
-      if (k >= 2) CK(cudaEventSynchronize(g.ev_h2d[s]));  // staging buffer free again
-      memcpy(g.h_in[s].p, in + off, len);
-      CK(cudaMemcpyAsync(g.in[s].p, g.h_in[s].p, len, cudaMemcpyHostToDevice, g.s_in));
-    }
-    CK(cudaEventRecord(g.ev_h2d[s], g.s_in));
-    CK(cudaStreamWaitEvent(g.s0, g.ev_h2d[s], 0));
-    if (k >= 2) CK(cudaStreamWaitEvent(g.s0, g.ev_d2h[s], 0));  // d_out[s] drained by slab k-2
-    CKS(dev_compress_contig(g.in[s].as<uint8_t>(), len, mode, g.out[s].as<uint8_t>(), 0, nullptr, g.s0));
-    CK(cudaMemcpyAsync(g.h_meta[s].p, g.d_total, 8, cudaMemcpyDeviceToHost, g.s0));
-    CK(cudaEventRecord(g.ev_comp[s], g.s0));
-    if (k >= 1) CKS(finish(k - 1));
   }
-  CKS(finish(nslab - 1));
+  const uint64_t slab_bytes = (uint64_t)kDevSlabChunks * kChunk;
+  const uint64_t nslab = (n + slab_bytes - 1) / slab_bytes;
+  const uint64_t piece_bytes = (uint64_t)kGroupChunks * kChunk;
+  const uint64_t pieces_per_slab = slab_bytes / piece_bytes;
+  const size_t per_block = mode == snb::kModeFrame ? (size_t)(kChunk + 8) : (size_t)SNB_MAX_COMPRESSED_FRAME_LEN;
+  const uint64_t slab0_chunks = (std::min<uint64_t>(n, slab_bytes) + kChunk - 1) / kChunk;
+  const int nbuf = nslab > 1 ? 2 : 1;
+  // every allocation happens before the first launch: cudaMalloc / cudaFree would wait for a spinning kernel
+  for (int i = 0; i < nbuf; i++) {
+    CK(g.in[i].ensure((size_t)std::min<uint64_t>(n, slab_bytes) + 64));
+    CK(g.out[i].ensure((size_t)slab0_chunks * per_block + 65536));
+    CK(g.h_flags[i].ensure((size_t)(pieces_per_slab + 1) * 8));
+  }
+  CK(g.h_arr.ensure((size_t)(nslab * pieces_per_slab + 1) * 4));
+  CK(g.h_meta[0].ensure(64));
+  {
+    const uint32_t slab = (uint32_t)slab0_chunks;
+    CK(g.scratch.ensure((size_t)slab * (mode == snb::kModeFrame ? kFrameStride : kRawStride) + 4096));
+    CK(g.lens.ensure((size_t)slab * 4));
+    CK(g.group_done.ensure(((size_t)slab / kGroupChunks + 2) * 4));
+    CK(g.group_end.ensure(((size_t)slab / kGroupChunks + 2) * 8));
+    CompressGeom cg = compress_geom((uint32_t)kChunk, slab);
+    CK(g.tables.ensure((size_t)cg.grid * cg.warps * cg.entries * 2 + 256));
+  }
+  uint32_t* h_arr = g.h_arr.as<uint32_t>();
+  // arrival counter and timeout flag start at zero, and no kernel of this call may look before that
+  CK(cudaMemsetAsync(g.d_arrived, 0, 2 * sizeof(uint32_t), g.s_in));
+  CK(cudaEventRecord(g.ev_reset, g.s_in));
+  CK(cudaStreamWaitEvent(g.s0, g.ev_reset, 0));
+
+  auto copy_in = [&](uint64_t k) -> int {
+    const int s = (int)(k & 1);
+    const uint64_t off = k * slab_bytes, len = std::min<uint64_t>(slab_bytes, n - off);
+    if (k >= 2) CK(cudaStreamWaitEvent(g.s_in, g.ev_comp[s], 0));  // in[s] consumed by slab k-2
+    uint64_t pi = k * pieces_per_slab;
+    for (uint64_t po = 0; po < len; po += piece_bytes, pi++) {
+      const uint64_t pl = std::min<uint64_t>(piece_bytes, len - po);
+      CK(cudaMemcpyAsync(g.in[s].as<uint8_t>() + po, in + off + po, pl, cudaMemcpyHostToDevice, g.s_in));
+      h_arr[pi] = (uint32_t)((off + po + pl + kChunk - 1) / kChunk);
+      CK(cudaMemcpyAsync(g.d_arrived, &h_arr[pi], 4, cudaMemcpyHostToDevice, g.s_in));
+    }
+    return SNB_OK;
+  };
+  auto launch = [&](uint64_t k) -> int {
+    const int s = (int)(k & 1);
+    const uint64_t off = k * slab_bytes, len = std::min<uint64_t>(slab_bytes, n - off);
+    memset(g.h_flags[s].p, 0, (size_t)(pieces_per_slab + 1) * 8);
+    if (k >= 2) CK(cudaStreamWaitEvent(g.s0, g.ev_d2h[s], 0));  // out[s] drained by slab k-2
+    CKS(dev_compress_stream(g.in[s].as<uint8_t>(), len, mode, g.out[s].as<uint8_t>(), 0, nullptr, g.s0, g.d_arrived,
+                            k * kDevSlabChunks, g.h_flags[s].as<unsigned long long>()));
+    CK(cudaEventRecord(g.ev_comp[s], g.s0));
+    return SNB_OK;
+  };
+  auto enqueue = [&](uint64_t k) -> int {
+#ifdef SNB_EMULATE
+    CKS(copy_in(k));   // the emulated runtime is synchronous: the input has to be there first
+    CKS(launch(k));
+#else
+    CKS(launch(k));    // the kernel waits for its pieces, so a (host-synchronous) pageable copy still overlaps it
+    CKS(copy_in(k));
+#endif
+    return SNB_OK;
+  };
+  auto drain = [&](uint64_t k) -> int {
+    const int s = (int)(k & 1);
+    const uint64_t off = k * slab_bytes, len = std::min<uint64_t>(slab_bytes, n - off);
+    const uint64_t chunks = (len + kChunk - 1) / kChunk, groups = (chunks + kGroupChunks - 1) / kGroupChunks;
+    volatile unsigned long long* flags = g.h_flags[s].as<unsigned long long>();
+    unsigned long long prev = 0, end = 0;
+    for (uint64_t gi = 0; gi < groups; gi++) {
+      CKS(wait_group_flag(flags + gi, g.ev_comp[s], &end));
+      if (end > prev) CK(cudaMemcpyAsync(out + *pos + prev, g.out[s].as<uint8_t>() + prev, end - prev, cudaMemcpyDeviceToHost, g.s_out));
+      prev = end;
+    }
+    CK(cudaEventRecord(g.ev_d2h[s], g.s_out));
+    *pos += end;
+    return SNB_OK;
+  };
+  CKS(enqueue(0));
+  for (uint64_t k = 0; k < nslab; k++) {
+    if (k + 1 < nslab) CKS(enqueue(k + 1));
+    CKS(drain(k));
+  }
+  CK(cudaMemcpyAsync(g.h_meta[0].p, g.d_arrived + 1, 4, cudaMemcpyDeviceToHost, g.s0));
+  CK(cudaStreamSynchronize(g.s_in));
+  CK(cudaStreamSynchronize(g.s0));
   CK(cudaStreamSynchronize(g.s_out));
-  (void)slab_len;
+  if (*g.h_meta[0].as<uint32_t>() != 0) { g.err = "streaming compress: timed out waiting for input pieces"; return SNB_CUDA_ERROR; }
   return SNB_OK;
 }
 
@@ -625,10 +765,11 @@ void snb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.ready) return;
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.tables, &g.in[0], &g.in[1], &g.out[0], &g.out[1]})
+  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.tables, &g.in[0], &g.in[1], &g.out[0], &g.out[1], &g.group_done, &g.group_end})
     b->release();
-  for (PinBuf* b : {&g.h_in[0], &g.h_in[1], &g.h_out[0], &g.h_out[1], &g.h_meta[0], &g.h_meta[1]}) b->release();
-  cudaFree(g.d_tables); cudaFree(g.d_hdr); cudaFree(g.d_counters); cudaFree(g.d_total);
+  for (PinBuf* b : {&g.h_in[0], &g.h_in[1], &g.h_out[0], &g.h_out[1], &g.h_meta[0], &g.h_meta[1], &g.h_flags[0], &g.h_flags[1], &g.h_arr}) b->release();
+  cudaFree(g.d_tables); cudaFree(g.d_hdr); cudaFree(g.d_counters); cudaFree(g.d_total); cudaFree(g.d_arrived);
+  cudaEventDestroy(g.ev_reset);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(g.ev_h2d[i]); cudaEventDestroy(g.ev_comp[i]); cudaEventDestroy(g.ev_d2h[i]); }
   for (int i = 0; i < 12; i++) cudaEventDestroy(g.ev_prof[i]);
   cudaStreamDestroy(g.s0); cudaStreamDestroy(g.s_in); cudaStreamDestroy(g.s_out);
@@ -782,7 +923,8 @@ int snb_dev_compress_framed(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uin
   if (n == 0) {
     CK(cudaMemcpyAsync(g.d_total, &base, 8, cudaMemcpyHostToDevice, st));
   } else {
-    CKS(dev_compress_contig(d_in, n, snb::kModeFrame, d_out, base, d_frame_lens, st));
+    if (use_v5()) CKS(dev_compress_stream(d_in, n, snb::kModeFrame, d_out, base, d_frame_lens, st, nullptr, 0, nullptr));
+    else CKS(dev_compress_contig(d_in, n, snb::kModeFrame, d_out, base, d_frame_lens, st));
   }
   if (d_written) CK(cudaMemcpyAsync(d_written, g.d_total, 8, cudaMemcpyDeviceToDevice, st));
   if (written || g.profiling) {
@@ -790,7 +932,7 @@ int snb_dev_compress_framed(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uin
     CK(cudaMemcpyAsync(g.h_meta[0].p, g.d_total, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (written) *written = *g.h_meta[0].as<uint64_t>();
-    if (n) prof_collect(0, 4, 0);
+    if (n) { if (use_v5()) prof_collect(2, 1, 1); else prof_collect(0, 4, 0); }
     g.prof[5] = (float)g.call_launches;
   }
   return SNB_OK;

@@ -1444,8 +1444,8 @@ __device__ __forceinline__ uint32_t encode_block(uint32_t algo, const uint8_t* i
 // One job = one encodeFrame (encoder.nim:385-426), one bare encodeBlock, or one whole
 // single-block `compress` message (snappy.nim:27-64).
 template <int kAlgo>
-__device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job, uint16_t* table, uint32_t lane,
-                                             uint32_t stage, bool tglobal) {
+__device__ __forceinline__ uint32_t compress_job(const CompressArgs& a, uint32_t job, uint16_t* table, uint32_t lane,
+                                                 uint32_t stage, bool tglobal, uint32_t crc_in = 0, bool publish = true) {
   uint64_t ioff = a.in_off ? a.in_off[job] : (uint64_t)job * kMaxBlock;
   uint32_t len = a.in_len ? a.in_len[job] : (uint32_t)((a.total_len - ioff) < kMaxBlock ? (a.total_len - ioff) : kMaxBlock);
   uint64_t ooff = a.out_off ? a.out_off[job] : (uint64_t)job * a.out_stride;
@@ -1460,7 +1460,7 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
   if (frame ? len >= kMinNonLiteral : len > 0) bl = encode_block<kAlgo>(a.algo, in, len, out + pre, table, thr, lane, stage, tglobal);  // encoder.nim:401-406
   uint32_t total;
   if (frame) {
-    uint32_t crc = a.crc[job];
+    uint32_t crc = a.crc ? a.crc[job] : crc_in;
     uint32_t fl;
     if (bl != kAborted && bl <= thr) {  // :408-416
       put_varint32(out + 8, len, lane);
@@ -1480,7 +1480,8 @@ __device__ __forceinline__ void compress_job(const CompressArgs& a, uint32_t job
     if (a.mode == kModeRawMessage) put_varint32(out, len, lane);  // snappy.nim:49-50
     total = hl + bl;
   }
-  if (lane == 0) a.out_len[job] = total;
+  if (publish && lane == 0) a.out_len[job] = total;
+  return total;
 }
 
 // Persistent kernel: blockDim.x/32 warps per CTA pulling jobs from a global counter.  The first
@@ -1530,6 +1531,193 @@ __global__ void __launch_bounds__(kCompress5MaxThreads, 1) compress_kernel5(Comp
     if (job >= a.count) return;
     compress_job<5>(a, job, table, lane, 0, tglobal);
     __syncwarp();
+  }
+}
+
+// --------------------------------------------------------------------- streaming compress (one launch per slab)
+// One persistent kernel does everything `compressFramed` needs for a slab of chunks (snappy.nim:130-155):
+//
+//   arrive   a job may start before the whole input is in HBM: the host copies the input in pieces and
+//            bumps `arrived` (chunks landed) after each piece; the warp that dequeues chunk j waits for it.
+//   crc      masked CRC-32C of the chunk (codec.nim:71-75) by the same warp -- this sequential pass also
+//            pulls the chunk into L2 for the parse that follows.
+//   encode   compress_block_v5 into the chunk's scratch slot (encodeFrame, encoder.nim:385-426).
+//   pack     frames are concatenated in chunk order.  `frontier` holds (next chunk to place, its offset);
+//            a warp that has just published its frame length places every consecutive chunk whose length
+//            is known (CAS on the frontier), copying slot -> final position.  Nobody ever waits for
+//            another warp: the publisher of the chunk the frontier is stuck at picks up the backlog.
+//   signal   chunks are grouped (1 << group_shift); when every chunk of a group has been placed the
+//            group's end offset is written to host-mapped memory, and the host starts the D2H of that
+//            byte range while later chunks are still being encoded.
+struct StreamArgs {
+  CompressArgs c;                        // encoder geometry; c.out_base = scratch slots, c.out_len = frame lengths (zeroed)
+  uint8_t* dst;                          // packed output
+  unsigned long long* frontier;          // (offset << 24) | next chunk
+  const uint32_t* arrived;               // chunks whose input has landed (null: the input is resident)
+  uint32_t* group_done;                  // per group: chunks placed (zeroed)
+  unsigned long long* group_end;         // per group: end offset, written by whoever places its last chunk
+  unsigned long long* host_flags;        // per group, host-mapped: end offset + 1 once the group is complete (null: none)
+  unsigned long long* total;             // end offset of the slab (written when the last chunk is placed)
+  uint32_t* error;                       // set to 1 when a wait times out
+  const CrcTables* crc_tables;
+  uint32_t group_shift;
+  uint32_t chunk0;                       // index of this slab's first chunk in `arrived` units
+};
+
+#ifdef SNB_EMULATE
+__device__ __forceinline__ unsigned long long snb_now_ns() { return 0; }
+__device__ __forceinline__ void snb_sleep(unsigned) {}
+__device__ __forceinline__ uint32_t ld_cg32(const uint32_t* p) { return *p; }
+#else
+__device__ __forceinline__ unsigned long long snb_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void snb_sleep(unsigned ns) { __nanosleep(ns); }
+__device__ __forceinline__ uint32_t ld_cg32(const uint32_t* p) { return __ldcg(p); }
+#endif
+
+// Copy n bytes, any alignment, reading through L2 only (the source was written by another SM).
+__device__ __forceinline__ void warp_copy_cg(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) {
+  uint32_t head = umin32(n, (uint32_t)((0 - (uintptr_t)dst) & 15));
+  if (lane < head) dst[lane] = src[lane];
+  const uint32_t vecs = (n - head) >> 4;
+  const uint8_t* s = src + head;
+  const uint32_t sh = (uint32_t)((uintptr_t)s & 3) * 8;
+  const uint32_t* sw = (const uint32_t*)((uintptr_t)s & ~(uintptr_t)3);
+  uint4* dv = (uint4*)(dst + head);
+  for (uint32_t base = 0; base < vecs; base += 32) {   // uniform trip count: the shuffle below is convergent
+    const uint32_t i = base + lane;
+    const bool on = i < vecs;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    if (on) { w0 = ld_cg32(sw + 4 * i); w1 = ld_cg32(sw + 4 * i + 1); w2 = ld_cg32(sw + 4 * i + 2); w3 = ld_cg32(sw + 4 * i + 3); }
+    uint32_t w4 = __shfl_down_sync(kFull, w0, 1);
+    if (on && sh && (lane == 31 || i + 1 == vecs)) w4 = ld_cg32(sw + 4 * i + 4);
+    if (on) {
+      uint4 v;
+      v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+      v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+      dv[i] = v;
+    }
+  }
+  const uint32_t done = head + 16 * vecs;
+  if (lane < n - done) dst[done + lane] = src[done + lane];
+}
+
+__device__ __forceinline__ void stream_place(const StreamArgs& a, uint32_t lane) {
+  const uint32_t count = a.c.count;
+  for (;;) {
+    unsigned long long f = 0;
+    uint32_t len = 0, state = 0;   // 0: nothing to place, 1: lost the race (look again), 2: chunk claimed
+    if (lane == 0) {
+      f = *(volatile unsigned long long*)a.frontier;
+      const uint32_t idx = (uint32_t)(f & 0xffffffull);
+      if (idx < count) {
+        len = *(volatile uint32_t*)(a.c.out_len + idx);
+        if (len) {
+          const unsigned long long nf = (((f >> 24) + len) << 24) | (unsigned long long)(idx + 1);
+          state = atomicCAS(a.frontier, f, nf) == f ? 2u : 1u;
+          if (state == 2) __threadfence();   // the slot's bytes were published before its length
+        }
+      }
+    }
+    state = __shfl_sync(kFull, state, 0);
+    if (state == 0) return;
+    if (state == 1) continue;
+    __syncwarp();
+    const uint32_t idx = __shfl_sync(kFull, (uint32_t)(f & 0xffffffull), 0);
+    const uint32_t off_lo = __shfl_sync(kFull, (uint32_t)(f >> 24), 0), off_hi = __shfl_sync(kFull, (uint32_t)(f >> 56), 0);
+    const unsigned long long off = ((unsigned long long)off_hi << 32) | off_lo;
+    len = __shfl_sync(kFull, len, 0);
+    const uint8_t* slot = a.c.out_base + (unsigned long long)idx * a.c.out_stride;
+    uint8_t* d = a.dst + off;
+    const uint32_t first = ld_cg32((const uint32_t*)slot) & 0xff;
+    if (a.c.mode == kModeFrame && a.c.defer_stored && first == 0x01) {   // stored chunk: header from the slot, payload from the input
+      if (lane < 8) d[lane] = slot[lane];
+      warp_copy_cg(d + 8, a.c.in_base + (unsigned long long)idx * kMaxBlock, len - 8, lane);
+    } else {
+      warp_copy_cg(d, slot, len, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t grp = idx >> a.group_shift;
+      const uint32_t gfirst = grp << a.group_shift;
+      const uint32_t gsize = umin32(count - gfirst, 1u << a.group_shift);
+      const bool last_of_group = idx + 1 == gfirst + gsize;
+      if (last_of_group) *(volatile unsigned long long*)(a.group_end + grp) = off + len;
+      if (idx + 1 == count) *(volatile unsigned long long*)a.total = off + len;
+      __threadfence();
+      if (atomicAdd(a.group_done + grp, 1u) + 1 == gsize && a.host_flags) {
+        __threadfence();
+        const unsigned long long end = *(volatile unsigned long long*)(a.group_end + grp);
+        __threadfence_system();
+        *(volatile unsigned long long*)(a.host_flags + grp) = end + 1;
+      }
+    }
+  }
+}
+
+#ifndef SNB_STREAM_MAXT
+#define SNB_STREAM_MAXT 768
+#endif
+constexpr uint32_t kStreamMaxThreads = SNB_STREAM_MAXT;
+constexpr unsigned long long kArriveTimeoutNs = 20ull * 1000 * 1000 * 1000;
+__global__ void __launch_bounds__(kStreamMaxThreads, 1) compress_stream_kernel(StreamArgs a) {
+  SNB_DYN_SMEM(smem);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool tglobal = warp >= a.c.smem_warps;
+  uint16_t* table = !tglobal
+                        ? (uint16_t*)smem + (size_t)warp * a.c.table_entries
+                        : a.c.gtables + ((size_t)blockIdx.x * (blockDim.x / 32 - a.c.smem_warps) + (warp - a.c.smem_warps)) * a.c.table_entries;
+  CrcSmem* crc_t = (CrcSmem*)(smem + (size_t)a.c.smem_warps * a.c.table_entries * 2);
+  const bool frame = a.c.mode == kModeFrame;
+  if (frame) crc_stage_tables(crc_t, a.crc_tables);
+  for (;;) {
+    uint32_t job = 0;
+    if (lane == 0) job = atomicAdd(a.c.counter, 1u);
+    job = __shfl_sync(kFull, job, 0);
+    if (job >= a.c.count) return;
+    if (a.arrived) {  // the chunk's bytes may still be on their way
+      if (lane == 0) {
+        const volatile uint32_t* arr = (const volatile uint32_t*)a.arrived;
+        if (*arr <= a.chunk0 + job) {
+          const unsigned long long t0 = snb_now_ns();
+          while (*arr <= a.chunk0 + job) {
+            snb_sleep(500);
+            if (snb_now_ns() - t0 > kArriveTimeoutNs) { *(volatile uint32_t*)a.error = 1; break; }
+          }
+        }
+        __threadfence();
+      }
+      __syncwarp();
+    }
+    uint32_t crc = 0;
+    if (frame) {
+      const unsigned long long ioff = (unsigned long long)job * kMaxBlock;
+      const uint32_t len = (uint32_t)((a.c.total_len - ioff) < kMaxBlock ? (a.c.total_len - ioff) : kMaxBlock);
+      crc = crc_mask(crc32c_warp(*crc_t, a.crc_tables, a.c.in_base + ioff, len, lane));
+    }
+    const uint32_t total = compress_job<5>(a.c, job, table, lane, 0, tglobal, crc, false);
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();   // the frame's bytes before its length
+      *(volatile uint32_t*)(a.c.out_len + job) = total;
+      __threadfence();   // ... and the length before this warp looks at the frontier
+    }
+    __syncwarp();
+    stream_place(a, lane);
+    __syncwarp();
+  }
+}
+
+// frontier = (base << 24) for the first slab, or continues at *prev_total.
+__global__ void stream_init_kernel(unsigned long long* frontier, const unsigned long long* prev_total,
+                                   unsigned long long base, unsigned long long* total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const unsigned long long b = prev_total ? *prev_total : base;
+    *frontier = b << 24;
+    *total = b;
   }
 }
 

@@ -253,5 +253,9 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 static inline void __threadfence() {}
+static inline void __threadfence_system() {}
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
+  unsigned long long o = *p; if (o == cmp) *p = v; return o;
+}
 static inline unsigned umin(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned umax(unsigned a, unsigned b) { return a > b ? a : b; }
