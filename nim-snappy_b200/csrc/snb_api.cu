@@ -8,6 +8,7 @@
 #include "../../include/snb.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <string>
@@ -73,19 +74,20 @@ struct Ctx {
   bool ready = false;
   int device = 0, sms = 148;
   cudaStream_t s0 = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_dec[4] = {nullptr, nullptr, nullptr, nullptr};   // host decode pipeline: slabs in flight decode concurrently
   snb::CrcTables h_tables;
   snb::CrcTables* d_tables = nullptr;
   uint8_t* d_hdr = nullptr;
   uint32_t* d_counters = nullptr;
   int counter_next = 0;
   uint64_t* d_total = nullptr;  // 4 device scalars
-  DevBuf scratch, lens, offs, crcs, chunks, status, outlen, tables, in[2], out[2];
-  PinBuf h_in[2], h_out[2], h_meta[2];
+  DevBuf scratch, lens, offs, crcs, chunks, status, outlen, tables, in[4], out[4];
+  PinBuf h_in[4], h_out[4], h_meta[4];
   DevBuf group_done, group_end;     // streaming compress: per-group placement counters / end offsets
   PinBuf h_flags[2], h_arr;         // host-mapped group-complete flags per slab parity; arrival values per piece
   uint32_t* d_arrived = nullptr;    // chunks whose input has landed (streaming compress), then a timeout flag
   cudaEvent_t ev_reset = nullptr;
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[4] = {}, ev_comp[4] = {}, ev_d2h[4] = {};
   cudaEvent_t ev_prof[12] = {};
   bool profiling = false;
   float prof[6] = {0, 0, 0, 0, 0, 0};
@@ -94,6 +96,10 @@ struct Ctx {
   int compress_warps = 4;    // 64 KiB blocks: encoder warps per SM with the table in shared memory (more would squeeze the L1 below what the candidate loads need)
   int compress_gwarps = 20;  // ... and with the table in global memory (L2)
   int compress_algo = 0;  // 0 auto (= 5), 1/2/4/5 warp encoders v1/v2/v3/v5, 3 one thread per block
+  size_t l2_persist_max = 0, l2_window_max = 0;   // device limits for the L2 access-policy window (0: unsupported)
+  int l2_tables = 1;                              // keep the encoder's global-memory hash tables resident in L2
+  float l2_ratio = 0.f;                           // 0: derive from the carve-out and the table bytes
+  uint32_t dec_slab_chunks = 1024;  // host decode pipeline: chunks per H2D | kernel | D2H slab (64 MiB of output: short fill / drain)
   int thread_min_chunks = 1 << 30;  // auto mode: batches at least this large use one thread per block (tables in HBM)
   std::string err;
 };
@@ -194,11 +200,28 @@ int do_init(int device) {
   CK(cudaSetDevice(device));
   g.device = device;
   CK(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, device));
-  if (const char* e = getenv("SNB_TUNE_SMS")) g.sms = std::max(1, atoi(e));   // tuning experiments only: persistent grids use this many SMs
+  // tuning experiments only: persistent grids use this many SMs / chunks per slab of the host decode pipeline
+  if (const char* e = getenv("SNB_TUNE_SMS")) g.sms = std::max(1, atoi(e));
+  if (const char* e = getenv("SNB_TUNE_DEC_SLAB")) g.dec_slab_chunks = (uint32_t)std::min<int>(kHostSlabChunks, std::max(1, atoi(e)));
+#ifndef SNB_EMULATE
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    g.l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    g.l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (const char* e = getenv("SNB_TUNE_L2_TABLES")) g.l2_tables = atoi(e);
+    if (const char* e = getenv("SNB_TUNE_L2_RATIO")) g.l2_ratio = (float)atof(e);
+    size_t want = g.l2_persist_max;
+    if (const char* e = getenv("SNB_TUNE_L2_MB")) want = std::min(want, (size_t)atoi(e) << 20);
+    if (g.l2_tables && want) { CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want)); g.l2_persist_max = want; }
+    if (getenv("SNB_TUNE_VERBOSE")) fprintf(stderr, "snb: L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", prop.l2CacheSize >> 20, g.l2_persist_max >> 20, g.l2_window_max >> 20);
+  }
+#endif
   CK(cudaStreamCreateWithFlags(&g.s0, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&g.s_out, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 4; i++) {
+    CK(cudaStreamCreateWithFlags(&g.s_dec[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.ev_h2d[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_comp[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_d2h[i], cudaEventDisableTiming));
@@ -410,6 +433,24 @@ int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
     a.total = d_total; a.error = g.d_arrived + 1; a.crc_tables = g.d_tables;
     a.group_shift = kGroupShift; a.chunk0 = (uint32_t)(chunk0 + first);
     if (p) prof_mark(2, st);
+#ifndef SNB_EMULATE
+    const size_t tbytes = (size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2;
+    if (g.l2_tables && g.l2_persist_max && g.l2_window_max && tbytes) {
+      // the global-memory hash tables are the only randomly re-read data: pin them in L2, let everything else stream
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(std::min(cg.grid, (uint32_t)g.sms)); cfg.blockDim = dim3(cg.warps * 32);
+      cfg.dynamicSmemBytes = cg.smem; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+      at[0].val.accessPolicyWindow.base_ptr = g.tables.p;
+      at[0].val.accessPolicyWindow.num_bytes = std::min(tbytes, g.l2_window_max);
+      at[0].val.accessPolicyWindow.hitRatio = g.l2_ratio > 0.f ? g.l2_ratio : std::min(1.0f, (float)g.l2_persist_max / (float)tbytes);
+      at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, snb::compress_stream_kernel, a));
+    } else
+#endif
     SNB_LAUNCH(snb::compress_stream_kernel, std::min(cg.grid, (uint32_t)g.sms), cg.warps * 32, cg.smem, st, a);
     count_launch();
     CK(cudaGetLastError());
@@ -665,20 +706,25 @@ int host_crc(const uint8_t* buf, size_t n, uint32_t* crc_out) {
 inline uint32_t mask_crc(uint32_t c) { return ((c >> 15) | (c << 17)) + snb::kCrcMaskDelta; }
 
 // Decode the walked chunks: slabs of chunks bounded by device buffer sizes, H2D | kernel | D2H.
+// One chunk is one warp's serial job (~2 ms for 64 KiB of text), so a slab's kernel cannot finish faster
+// than that however small the slab: up to kDecInFlight slabs are in flight, each kernel on its own stream,
+// so that they overlap each other and the copies (H2D in order on s_in, D2H in order on s_out).
 // first_bad receives the index of the first chunk with a non-zero status (or -1).
+constexpr int kDecInFlight = 4;
 int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_t* out, int verify,
                        int64_t* first_bad, int32_t* bad_status) {
   *first_bad = -1;
   const size_t count = chunks.size();
   if (!count) return SNB_OK;
   const bool pin_in = is_pinned(in), pin_out = is_pinned(out);
-  const uint64_t in_budget = (uint64_t)kHostSlabChunks * kChunk + 2 * SNB_MAX_COMPRESSED_FRAME_LEN;
+  const uint32_t slab_chunks = g.dec_slab_chunks;
+  const uint64_t in_budget = (uint64_t)slab_chunks * kChunk + 2 * SNB_MAX_COMPRESSED_FRAME_LEN;
   size_t i = 0;
   uint64_t k = 0;
   struct Pending { size_t first, cnt; uint64_t out_begin, out_len; };
-  Pending pend[2];
+  Pending pend[kDecInFlight];
   auto finish = [&](uint64_t kk) -> int {
-    int s = (int)(kk & 1);
+    int s = (int)(kk % kDecInFlight);
     Pending& p = pend[s];
     CK(cudaEventSynchronize(g.ev_d2h[s]));
     if (!pin_out && p.out_len) memcpy(out + p.out_begin, g.h_out[s].p, p.out_len);
@@ -687,26 +733,26 @@ int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_
       if (st[j] != 0) { *first_bad = (int64_t)(p.first + j); *bad_status = st[j]; }
     return SNB_OK;
   };
+  CK(g.chunks.ensure((size_t)kDecInFlight * kHostSlabChunks * sizeof(snb_chunk)));
+  CK(g.status.ensure((size_t)kDecInFlight * kHostSlabChunks * 4));
+  CK(g.outlen.ensure((size_t)kDecInFlight * kHostSlabChunks * 4));
   while (i < count && *first_bad < 0) {
-    // slab = chunks [i, j): contiguous input range within budget, at most kHostSlabChunks chunks
+    // slab = chunks [i, j): contiguous input range within budget, at most slab_chunks chunks
     size_t j = i;
     uint64_t in_begin = chunks[i].in_off, in_end = in_begin, out_begin = chunks[i].out_off, out_end = out_begin;
-    while (j < count && j - i < kHostSlabChunks) {
+    while (j < count && j - i < slab_chunks) {
       uint64_t e = chunks[j].in_off + chunks[j].in_len;
       if (j > i && e - in_begin > in_budget) break;
       in_end = e;
       if (chunks[j].kind != snb::kKindVerifyOnly) out_end = chunks[j].out_off + chunks[j].out_cap;
       j++;
     }
-    int s = (int)(k & 1);
+    const int s = (int)(k % kDecInFlight);
     size_t cnt = j - i;
     uint64_t in_len = in_end - in_begin, out_len = out_end - out_begin;
-    if (k >= 2) CKS(finish(k - 2));  // frees slot s (host staging + meta)
+    if (k >= (uint64_t)kDecInFlight) CKS(finish(k - kDecInFlight));  // frees slot s (device buffers, host staging + meta)
     CK(g.in[s].ensure(in_len + 64));
     CK(g.out[s].ensure(out_len + 64));
-    CK(g.chunks.ensure(2 * kHostSlabChunks * sizeof(snb_chunk)));
-    CK(g.status.ensure(2 * kHostSlabChunks * 4));
-    CK(g.outlen.ensure(2 * kHostSlabChunks * 4));
     CK(g.h_meta[s].ensure(cnt * (sizeof(snb_chunk) + 4)));
     if (!pin_in) CK(g.h_in[s].ensure(in_len));
     if (!pin_out) CK(g.h_out[s].ensure(out_len));
@@ -727,10 +773,11 @@ int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_
     }
     CK(cudaMemcpyAsync(d_chunks, hm, cnt * sizeof(snb_chunk), cudaMemcpyHostToDevice, g.s_in));
     CK(cudaEventRecord(g.ev_h2d[s], g.s_in));
-    CK(cudaStreamWaitEvent(g.s0, g.ev_h2d[s], 0));
+    cudaStream_t sc = g.s_dec[s];
+    CK(cudaStreamWaitEvent(sc, g.ev_h2d[s], 0));
     CKS(launch_decompress(g.in[s].as<uint8_t>(), g.out[s].as<uint8_t>(), d_chunks, (uint32_t)cnt, verify, d_status,
-                          d_outlen, g.s0));
-    CK(cudaEventRecord(g.ev_comp[s], g.s0));
+                          d_outlen, sc));
+    CK(cudaEventRecord(g.ev_comp[s], sc));
     CK(cudaStreamWaitEvent(g.s_out, g.ev_comp[s], 0));
     if (out_len) {
       CK(cudaMemcpyAsync(pin_out ? (void*)(out + out_begin) : g.h_out[s].p, g.out[s].p, out_len,
@@ -742,12 +789,10 @@ int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_
     pend[s] = Pending{i, cnt, out_begin, out_len};
     i = j;
     k++;
-    // the next slab reuses the other slot: its previous occupant (k-2) is finished at the loop top
   }
-  if (k >= 2) CKS(finish(k - 2));
-  if (k >= 1) CKS(finish(k - 1));
+  for (uint64_t kk = k > (uint64_t)kDecInFlight ? k - kDecInFlight : 0; kk < k; kk++) CKS(finish(kk));
   CK(cudaStreamSynchronize(g.s_in));
-  CK(cudaStreamSynchronize(g.s0));
+  for (int t = 0; t < kDecInFlight; t++) CK(cudaStreamSynchronize(g.s_dec[t]));
   CK(cudaStreamSynchronize(g.s_out));
   return SNB_OK;
 }
@@ -765,12 +810,13 @@ void snb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.ready) return;
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.tables, &g.in[0], &g.in[1], &g.out[0], &g.out[1], &g.group_done, &g.group_end})
+  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.tables, &g.group_done, &g.group_end})
     b->release();
-  for (PinBuf* b : {&g.h_in[0], &g.h_in[1], &g.h_out[0], &g.h_out[1], &g.h_meta[0], &g.h_meta[1], &g.h_flags[0], &g.h_flags[1], &g.h_arr}) b->release();
+  for (int i = 0; i < 4; i++) { g.in[i].release(); g.out[i].release(); g.h_in[i].release(); g.h_out[i].release(); g.h_meta[i].release(); }
+  for (PinBuf* b : {&g.h_flags[0], &g.h_flags[1], &g.h_arr}) b->release();
   cudaFree(g.d_tables); cudaFree(g.d_hdr); cudaFree(g.d_counters); cudaFree(g.d_total); cudaFree(g.d_arrived);
   cudaEventDestroy(g.ev_reset);
-  for (int i = 0; i < 2; i++) { cudaEventDestroy(g.ev_h2d[i]); cudaEventDestroy(g.ev_comp[i]); cudaEventDestroy(g.ev_d2h[i]); }
+  for (int i = 0; i < 4; i++) { cudaEventDestroy(g.ev_h2d[i]); cudaEventDestroy(g.ev_comp[i]); cudaEventDestroy(g.ev_d2h[i]); cudaStreamDestroy(g.s_dec[i]); }
   for (int i = 0; i < 12; i++) cudaEventDestroy(g.ev_prof[i]);
   cudaStreamDestroy(g.s0); cudaStreamDestroy(g.s_in); cudaStreamDestroy(g.s_out);
   g.ready = false;

@@ -41,8 +41,10 @@ enum : uint32_t { kKindCompressed = 0, kKindStored = 1, kKindVerifyOnly = 2 };
 #ifdef SNB_STATS
 __device__ unsigned long long g_stats[16];
 #define SNB_STAT(i) do { if (lane == 0) atomicAdd(&g_stats[i], 1ull); } while (0)
+#define SNB_STATN(i, n) do { if (lane == 0) atomicAdd(&g_stats[i], (unsigned long long)(n)); } while (0)
 #else
 #define SNB_STAT(i) do { } while (0)
+#define SNB_STATN(i, n) do { } while (0)
 #endif
 
 __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -1167,10 +1169,12 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     __syncwarp();  // table writes (zeroing / previous commit / serial step) visible to every lane
     const uint32_t b = (chain ? ip : pp) & ~31u;
 
+    SNB_STAT(8);
     if (force_slow || b + 32 >= ip_limit || (!chain && k >= 32)) {
       force_slow = false;
       m1_done = false;
       if (chain) {
+        SNB_STAT(1);
         // ---- one serial chain step straight on the table (encoder.nim:364-380)
         const uint32_t d1 = in_ld4(v, ip - 1), d = in_ld4(v, ip);
         const uint32_t h1 = hash14(d1, mask), hh = hash14(d, mask);
@@ -1187,6 +1191,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
         continue;
       }
       // ---- serial literal scan from (pp, k): 32 strided probes per step (encoder.nim:281-331)
+      SNB_STAT(2);
       uint32_t wip = pp, wskip = 32 + k;
       uint32_t hit_ip = 0, hit_cand = 0;
       bool found = false;
@@ -1245,6 +1250,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     m1_done = false;
 
     // ---- resolve
+    SNB_STAT(0);
     const uint32_t W = (Wn_b == b) ? Wn : __ldg(v.w + (b >> 2) + wlane);
     Wn = __ldg(v.w + umin32((b >> 2) + 8 + wlane, v.last));
     Wn_b = b + 32;
@@ -1299,8 +1305,9 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       const uint32_t q0 = qh ? (uint32_t)__ffs((int)qh) - 1u : 32u;
       const uint32_t run = range & (q0 >= 32 ? 0xffffffffu : ((2u << q0) - 1u));   // probes performed
       const uint32_t stale = __ballot_sync(kFull, (eg & run) != 0) & run;
-      if (stale) { force_slow = true; continue; }
+      if (stale) { SNB_STAT(5); force_slow = true; continue; }
       if (q0 >= 32) {  // every probe missed: insert them and move on (k == 32 switches to the strided scan)
+        SNB_STAT(6);
         if (((run >> lane) & 1u) && ((grp & run) >> lane) == 1u) table[h] = (uint16_t)p;
         k += (uint32_t)__popc(run);
         pp = b + bend;
@@ -1321,6 +1328,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
 
     bool done = false;  // block finished inside this pass (ip > ip_limit after a copy)
     for (;;) {          // one batch per turn; a match that reaches the horizon ends a batch
+      SNB_STAT(3);
       uint32_t A = 0, cc = c;
       do { A |= 1u << cc; cc = __shfl_sync(kFull, J, (int)cc); } while (cc < 32);
       bool onp = (A >> lane) & 1u;
@@ -1329,6 +1337,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       const uint32_t stale = __ballot_sync(kFull, ((LK >> lane) & 1u) && (eg & (ins | insb)) != 0);
       uint32_t slow_at = 32;
       if (stale) {  // keep the arrivals whose lookups all precede the first stale lane
+        SNB_STAT(9);
         const uint32_t xs = (uint32_t)__ffs((int)stale) - 1u;
         slow_at = 31u - (uint32_t)__clz((int)(A & ((2u << xs) - 1u)));
         A &= (1u << slow_at) - 1u;
@@ -1339,6 +1348,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       }
       ins |= insb;
       noprev = 0;
+      SNB_STATN(7, __popc(A));
       const uint32_t Ev = LK & HB;
       uint32_t EvT = Ev, tail = 0;
       if (cc >= 64 && cc < 96) EvT &= ~(1u << (cc - 64));                        // its copy is emitted below
@@ -1367,6 +1377,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       }
       // ---- the copy at lane e is at least 12 bytes long: measured with the whole warp (encoder.nim:130-182)
       const uint32_t e = cc - 64;
+      SNB_STAT(4);
       const uint32_t cand = __shfl_sync(kFull, T, (int)e);
       const uint32_t m = 12 + common_prefix_v2(v, len, cand + 12, b + e + 12, lane);
       op += emit_copy_v2(out + op, b + e - cand, m, lane);
