@@ -364,7 +364,7 @@ def run_ours(args):
                    "l2_policy": "inputs (1 GiB/GPU) larger than L2 (126 MB); no flush between steps",
                    "verified_vs_oracle": verified, "roundtrip_ok": roundtrip_ok},
         "clocks": clock_info,
-        "roofline": {"bound": "hbm", "kernel": "snb::compress_kernel", "achieved": round(alg_bytes / (ck_ms * 1e-3) / 1e9, 3),
+        "roofline": {"bound": "hbm", "kernel": "snb::compress_stream_kernel (CRC + encode + in-order pack, one launch per slab)", "achieved": round(alg_bytes / (ck_ms * 1e-3) / 1e9, 3),
                      "peak": peak, "unit": "GB/s", "frac": round(alg_bytes / (ck_ms * 1e-3) / 1e9 / peak, 5),
                      "traffic": (traffic or {}).get("compress_kernel_bytes_per_launch"),
                      "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": round(ck_ms, 4), "peak_source": peak_src,

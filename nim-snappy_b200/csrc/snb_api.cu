@@ -94,7 +94,7 @@ struct Ctx {
   uint64_t launches = 0;
   uint32_t call_launches = 0;
   int compress_warps = 4;    // 64 KiB blocks: encoder warps per SM with the table in shared memory (more would squeeze the L1 below what the candidate loads need)
-  int compress_gwarps = 20;  // ... and with the table in global memory (L2)
+  int compress_gwarps = 18;  // ... and with the table in global memory (L2); 18 measured best on text (round 1f sweep), 20 on mixed data
   int compress_algo = 0;  // 0 auto (= 5), 1/2/4/5 warp encoders v1/v2/v3/v5, 3 one thread per block
   size_t l2_persist_max = 0, l2_window_max = 0;   // device limits for the L2 access-policy window (0: unsupported)
   int l2_tables = 1;                              // keep the encoder's global-memory hash tables resident in L2
@@ -468,9 +468,10 @@ int launch_decompress(const uint8_t* d_in, uint8_t* d_out, const snb::Chunk* d_c
   a.in_base = d_in; a.out_base = d_out; a.chunks = d_chunks; a.status = d_status; a.out_len = d_outlen;
   a.count = count; a.verify = verify ? 1u : 0u;
   CKS(next_counter(st, &a.counter));
-  uint32_t grid = std::max(1u, std::min((count + 7) / 8, (uint32_t)g.sms * 8));
+  const uint32_t wpb = snb::kDecThreads / 32;
+  uint32_t grid = std::max(1u, std::min((count + wpb - 1) / wpb, (uint32_t)g.sms * snb::kDecBlocksPerSm * 2));
   prof_mark(8, st);
-  SNB_LAUNCH(snb::decompress_kernel, grid, 256, 0, st, a, g.d_tables);
+  SNB_LAUNCH(snb::decompress_kernel, grid, snb::kDecThreads, 0, st, a, g.d_tables);
   count_launch();
   CK(cudaGetLastError());
   prof_mark(9, st);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Quick A/B on the GPU: compress kernel variants (algo, warps per CTA) on a corpus; every
 variant's output is compared with the oracle stream.
-Usage: python scripts/gpu_tune.py [MiB] [text|mixed] [algo:warps,...]"""
+Usage: python scripts/gpu_tune.py [MiB] [text|mixed|random|proto] [algo:warps,...]"""
 import os
 import sys
 
@@ -20,7 +20,16 @@ from nim_snappy_b200.workloads import mixed_corpus, text_corpus
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 kind = sys.argv[2] if len(sys.argv) > 2 else "text"
 n = mib << 20
-data = text_corpus(n) if kind == "text" else mixed_corpus(n, seed=1)
+if kind == "text":
+    data = text_corpus(n)
+elif kind == "mixed":
+    data = mixed_corpus(n, seed=1)
+elif kind == "random":
+    import numpy as np
+    data = np.random.default_rng(3).integers(0, 256, n, dtype=np.uint8)
+else:  # "proto"
+    from nim_snappy_b200.workloads import PROTO_FILES, _cat, tile
+    data = tile(_cat(PROTO_FILES), n)
 ref = CpuReference()
 _, stream = ref.framed_stream(data)
 lib = _lib.default()
