@@ -57,6 +57,11 @@ int snb_is_framed_stream(const uint8_t *in, size_t n);
 
 /* ---- host-buffer API: one call == one reference call -------------------------------------- */
 /* codec.nim:66-75 masked_crc32c / maskedCrc, computed on the GPU. */
+/* Page-locked host buffers for streaming callers (the faststreams entry points, faststreams.nim:20-153, keep a
+ * `tmp` block buffer per call; here the staging slabs are pinned so the copies are plain DMA).  NULL on failure. */
+void *snb_host_alloc(size_t n);
+void snb_host_free(void *p);
+
 int snb_masked_crc32c(const uint8_t *buf, size_t n, uint32_t *crc);
 /* snappy.nim:27-64 compress. */
 int snb_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);
@@ -64,7 +69,9 @@ int snb_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *
 int snb_uncompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);
 /* snappy.nim:130-155 compressFramed. */
 int snb_compress_framed(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);
-/* snappy.nim:169-267 uncompressFramed, including the resumable (read, written) contract. */
+/* snappy.nim:169-267 uncompressFramed, including the resumable (read, written) contract.  On a per-chunk failure
+ * (invalidInput / crcMismatch inside chunk k) *read / *written additionally report the intact prefix: the stream
+ * offset of chunk k's header and the bytes produced by chunks 0..k-1 (the reference's Result has no counts then). */
 int snb_uncompress_framed(const uint8_t *in, size_t n, uint8_t *out, size_t cap, int check_header,
                           int check_integrity, size_t *read, size_t *written);
 

@@ -6,3 +6,4 @@ from .codec import (CodecError, FrameError, framingHeader, maxCompressedLen,  # 
 from .snappy import (Snappy, compress, compressFramed, decode, decodeFramed, encode,  # noqa: F401
                      encodeFramed, isSnappyFramedStream, maskedCrc, uncompress, uncompressedLen,
                      uncompressedLenFramed, uncompressFramed)
+from . import faststreams  # noqa: F401,E402  (stream entry points, snappy/faststreams.nim)

@@ -53,6 +53,8 @@ SIGNATURES = {
     "snb_dev_uncompress_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snb_dev_uncompressed_lens": (_i, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "snb_dev_masked_crc32c_chunks": (_i, [_vp, _u64, _vp, _vp]),
+    "snb_host_alloc": (_vp, [_sz]),
+    "snb_host_free": (None, [_vp]),
     "snb_set_profiling": (None, [_i]),
     "snb_get_profile": (_i, [C.POINTER(C.c_float), _i]),
     "snb_kernel_launches": (_u64, []),

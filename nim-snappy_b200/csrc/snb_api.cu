@@ -941,15 +941,22 @@ int snb_uncompress_framed(const uint8_t* in, size_t n, uint8_t* out, size_t cap,
   int64_t bad = -1;
   int32_t bad_status = 0;
   CKS(host_decode_chunks(in, o.chunks, out, check_integrity, &bad, &bad_status));
-  if (bad >= 0) return bad_status == SNB_CRC_MISMATCH ? SNB_CRC_MISMATCH : SNB_INVALID_INPUT;
+  if (bad >= 0) {
+    // Beyond the reference (whose Result carries no counts on error): the intact prefix -- every chunk before the
+    // failing one is decoded and verified at its final place -- for callers that append chunk by chunk
+    // (faststreams.nim:116-132 writes each chunk before looking at the next).
+    *read = (size_t)(o.chunks[(size_t)bad].in_off - 8);
+    *written = (size_t)o.chunks[(size_t)bad].out_off;
+    return bad_status == SNB_CRC_MISMATCH ? SNB_CRC_MISMATCH : SNB_INVALID_INPUT;
+  }
   if (o.w.big_crc_len) {  // oversize stored chunk: crcMismatch outranks invalidInput (snappy.nim:244-251)
     uint32_t c = 0;
     CKS(host_crc(in + o.w.big_crc_off, (size_t)o.w.big_crc_len, &c));
     if (mask_crc(c) != o.w.big_crc) return SNB_CRC_MISMATCH;
   }
-  if (o.w.status) return o.w.status;
-  *read = (size_t)o.w.read;
+  *read = (size_t)o.w.read;       // on a header-level error: where the walk stopped / the intact prefix (see snb.h)
   *written = (size_t)o.w.written;
+  if (o.w.status) return o.w.status;
   return SNB_OK;
 }
 
@@ -1097,6 +1104,19 @@ uint64_t snb_kernel_launches(void) { return g.launches; }
 void snb_set_compress_warps(int warps) { g.compress_warps = warps % 100; if (warps >= 100) g.compress_gwarps = warps / 100 - 1; }
 void snb_set_compress_algo(int algo) { g.compress_algo = algo; }
 void snb_set_thread_min_chunks(int n) { g.thread_min_chunks = n; }
+
+// Page-locked host memory for callers that stream through the host-buffer entry points: pinned buffers are
+// DMA'd directly by snb_compress* / snb_uncompress* (is_pinned), pageable ones go through the driver's staging.
+void* snb_host_alloc(size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_init() != SNB_OK) return nullptr;
+  void* p = nullptr;
+  if (cudaMallocHost(&p, n ? n : 1) != cudaSuccess) { g.err = "snb_host_alloc: cudaMallocHost failed"; return nullptr; }
+  return p;
+}
+void snb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
 #ifdef SNB_STATS
 void snb_debug_stats(unsigned long long* out, int reset) {
   for (int i = 0; i < 16; i++) { out[i] = snb::g_stats[i]; if (reset) snb::g_stats[i] = 0; }

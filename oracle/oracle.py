@@ -230,3 +230,88 @@ class RefSnappyCpp:
 def ref_snappycpp():
     l = _load(os.path.join(HERE, "_ref", "libref_snappycpp.so"))
     return None if l is None else RefSnappyCpp(l)
+
+
+# ---------------------------------------------------------------- faststreams entry points (snappy/faststreams.nim)
+# Restated on top of the per-chunk oracle functions above.  Errors are reported by NAME (the reference raises
+# exception types, snappy/exceptions.nim:3-12); the bytes appended to the output stream before the error are
+# returned with it, because the reference writes chunk by chunk (faststreams.nim:13-18, :116-132).
+MAX_UNCOMPRESSED_FRAME = 65536          # codec.nim:14-19
+MAX_COMPRESSED_FRAME = 76490            # codec.nim:216-219
+FRAMING_HEADER = bytes([0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59])  # codec.nim:33-34
+
+
+def fs_compress(data):
+    """faststreams.nim:20-51 `compress(input, output)`: Leb128(len) then encodeBlock per 64 KiB.
+    -> (bytes, None) or (b"", "InputTooLarge")."""
+    a = _arr(data)
+    if a.size > 0xFFFFFFFF:               # :30-33 checkInputLen / maxCompressedLen
+        return b"", "InputTooLarge"
+    out = bytearray()
+    v = a.size
+    while v >= 0x80:                      # :37 toBytes(Leb128)
+        out.append((v & 0x7f) | 0x80)
+        v >>= 7
+    out.append(v)
+    for i in range(0, a.size, MAX_UNCOMPRESSED_FRAME):   # :44-51 (full blocks, then the remainder)
+        out += encode_block(a[i:i + MAX_UNCOMPRESSED_FRAME])
+    return bytes(out), None
+
+
+def fs_compress_framed(data):
+    """faststreams.nim:64-83 `compressFramed(input, output)`: framingHeader then encodeFrame per 64 KiB."""
+    a = _arr(data)
+    out = bytearray(FRAMING_HEADER)
+    tmp = np.empty(MAX_COMPRESSED_FRAME + 64, dtype=np.uint8)
+    for i in range(0, a.size, MAX_UNCOMPRESSED_FRAME):
+        blk = np.ascontiguousarray(a[i:i + MAX_UNCOMPRESSED_FRAME])
+        n = lib().orc_encode_frame(_ptr(blk), blk.size, _ptr(tmp))
+        out += tmp[:n].tobytes()
+    return bytes(out)
+
+
+def fs_uncompress_framed(data, check_integrity=True):
+    """faststreams.nim:85-147 `uncompressFramed(input, output, checkIntegrity)`.
+    -> (bytes appended to the output, None | "UnexpectedEofError" | "MalformedSnappyData")."""
+    b = bytes(data)
+    out = bytearray()
+    if len(b) < len(FRAMING_HEADER):                      # :88-89
+        return bytes(out), "UnexpectedEofError"
+    if b[:10] != FRAMING_HEADER:                          # :91-92
+        return bytes(out), "MalformedSnappyData"
+    pos = 10
+    while len(b) - pos >= 4:                              # :95
+        cid = b[pos]
+        data_len = b[pos + 1] | (b[pos + 2] << 8) | (b[pos + 3] << 16)   # codec.nim:166-172
+        pos += 4
+        if data_len > MAX_COMPRESSED_FRAME:               # :98-99
+            return bytes(out), "MalformedSnappyData"
+        if len(b) - pos < data_len:                       # :101-102
+            return bytes(out), "UnexpectedEofError"
+        if cid == 0x00:                                   # :104-117
+            if data_len < 4:
+                return bytes(out), "MalformedSnappyData"
+            crc = int.from_bytes(b[pos:pos + 4], "little")
+            st, dec = uncompress(b[pos + 4:pos + data_len], MAX_UNCOMPRESSED_FRAME)
+            if st != OK:
+                return bytes(out), "MalformedSnappyData"
+            if check_integrity and masked_crc32c(dec) != crc:
+                return bytes(out), "MalformedSnappyData"
+            out += dec
+        elif cid == 0x01:                                 # :119-129
+            if data_len < 4:
+                return bytes(out), "MalformedSnappyData"
+            if data_len - 4 > MAX_UNCOMPRESSED_FRAME:
+                return bytes(out), "MalformedSnappyData"
+            crc = int.from_bytes(b[pos:pos + 4], "little")
+            payload = b[pos + 4:pos + data_len]
+            if check_integrity and masked_crc32c(payload) != crc:
+                return bytes(out), "MalformedSnappyData"
+            out += payload
+        elif cid < 0x80:                                  # :131-135
+            return bytes(out), "MalformedSnappyData"
+        # else: skippable, including a repeated stream identifier (:137-140)
+        pos += data_len
+    if len(b) - pos >= 1:                                 # :142-143
+        return bytes(out), "MalformedSnappyData"
+    return bytes(out), None

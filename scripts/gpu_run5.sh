@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-for k in text mixed; do echo "#### $k"; MIB=1024 KIND=$k bash scripts/gpu_ab_libs.sh "5:1904" lib_d256_4.so lib_d128_9.so lib_d192_6.so lib_d128_10.so lib_d256_5.so; done
+for lib in lib_base.so libsnb200.so lib_base.so libsnb200.so; do echo "== $lib"; SNB_LIB=$PWD/nim-snappy_b200/$lib python scripts/gpu_e2e.py 1024 4 2>&1 | grep -v oracle; done | tee gpurun_out/e2e_ab.log

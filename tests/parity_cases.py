@@ -169,3 +169,86 @@ def mutate_streams(o, base, rng, count):
             b[i] = int(rng.integers(0, 256))
         out.append(bytes(b))
     return out
+
+
+# ---------------------------------------------------------------- faststreams entry points (snappy/faststreams.nim)
+class _NoLenReader:
+    """A non-seekable binary source handing out short reads (socket-like)."""
+
+    def __init__(self, data, piece):
+        self.d, self.p, self.piece = bytes(data), 0, piece
+
+    def read(self, n=-1):
+        k = self.piece if n < 0 else min(n, self.piece)
+        b = self.d[self.p:self.p + k]
+        self.p += len(b)
+        return b
+
+
+def _fs_decode(fs, stream, check_integrity=True, source=None):
+    """-> (bytes written to the output, exception class name | None)."""
+    import io
+    out = io.BytesIO()
+    try:
+        fs.uncompressFramed(stream if source is None else source, out, checkIntegrity=check_integrity)
+    except Exception as e:  # noqa: BLE001 -- the class name is the thing compared
+        return out.getvalue(), type(e).__name__
+    return out.getvalue(), None
+
+
+def check_faststreams(fs, o, datas):
+    """compress / compressFramed / uncompressFramed over streams == the oracle's restatement of
+    faststreams.nim:20-147 (bytes, and for the decoder the bytes written before an exception + its type)."""
+    import io
+    for d in datas:
+        out = io.BytesIO()
+        fs.compress(d, out)                                   # bytes-like input (faststreams.nim:55-57)
+        assert out.getvalue() == o.fs_compress(d)[0] == o.encode(d), len(d)
+        out = io.BytesIO()
+        fs.compress(io.BytesIO(d), out)                       # seekable stream input
+        assert out.getvalue() == o.encode(d), len(d)
+        want = o.fs_compress_framed(d)
+        assert want == o.encode_framed(d)
+        out = io.BytesIO()
+        fs.compressFramed(d, out)
+        assert out.getvalue() == want, len(d)
+        out = io.BytesIO()
+        fs.compressFramed(_NoLenReader(d, 50001), out)        # length unknown, short reads
+        assert out.getvalue() == want, len(d)
+        assert _fs_decode(fs, want) == (d, None)
+        assert _fs_decode(fs, want, source=_NoLenReader(want, 70001)) == (d, None)
+        assert _fs_decode(fs, want, source=io.BytesIO(want)) == (d, None)
+
+
+def check_faststreams_errors(fs, o):
+    """Exception parity (exceptions.nim:3-12) incl. what was written before the failure."""
+    small = o.encode_framed(b"hello hello hello hello hello")[10:]
+    two = o.encode_framed(bytes(range(256)) * 300)            # two chunks
+    zero = bytes(4)
+    data = bytes(65536)
+    big = bytes(65537)
+    cases = [
+        b"", HDR[:9],                                         # :88-89 UnexpectedEofError
+        b"\x00" + HDR[1:] + small,                            # :91-92 bad identifier
+        HDR, HDR + small, HDR + small + small,
+        HDR + small + b"\x00",                                # :142-143 trailing bytes
+        HDR + small + b"\x00\x00\x00",
+        HDR + small[:-1],                                     # :101-102 truncated frame
+        HDR + small + b"\x00\xff\xff\xff",                    # :98-99 dataLen > maxCompressedFrameDataLen
+        HDR + small + b"\x00\x03\x00\x00abc",                 # :105-106
+        HDR + small + b"\x01\x03\x00\x00abc",                 # :120-121
+        HDR + small + b"\x02\x01\x00\x00x" + small,           # :131-135 reserved unskippable
+        HDR + b"\x80\x01\x00\x00x" + small + b"\xfe\x02\x00\x00pp" + HDR + small,   # skippable + repeated identifier
+        HDR + small[:4] + zero + small[8:],                   # CRC mismatch, compressed
+        HDR + b"\x01" + (len(data) + 4).to_bytes(3, "little") + zero + data,          # CRC mismatch, stored
+        HDR + small + b"\x01" + (len(big) + 4).to_bytes(3, "little") + o.masked_crc32c(big).to_bytes(4, "little") + big,
+        HDR + small + b"\x00\x08\x00\x00" + zero + b"\x05\xff\xff\xff",               # malformed body after a good chunk
+        two[:-3], two + small[:5],
+        two[:10 + 4] + zero + two[10 + 8:],                   # first chunk's CRC wrong
+    ]
+    for i, s in enumerate(cases):
+        for ci in (True, False):
+            want = o.fs_uncompress_framed(s, ci)
+            got = _fs_decode(fs, s, ci)
+            assert got == want, (i, ci, got[1], want[1], len(got[0]), len(want[0]))
+        assert _fs_decode(fs, s, source=_NoLenReader(s, 7)) == o.fs_uncompress_framed(s, True), i
