@@ -315,3 +315,24 @@ def fs_uncompress_framed(data, check_integrity=True):
     if len(b) - pos >= 1:                                 # :142-143
         return bytes(out), "MalformedSnappyData"
     return bytes(out), None
+
+
+def st_compress(reads, input_len):
+    """streams.nim:9-41 `compress(input: Stream, inputLen, output: Stream)`: Leb128(inputLen), then one encodeBlock
+    per readData result (`reads`: the byte strings the stream hands out for successive 64 KiB requests) until
+    inputLen bytes have been seen.  -> (bytes, None) or (b"", "InputTooLarge")."""
+    if input_len < 0 or input_len > 0xFFFFFFFF:
+        return b"", "InputTooLarge"
+    out = bytearray()
+    v = input_len
+    while v >= 0x80:
+        out.append((v & 0x7f) | 0x80)
+        v >>= 7
+    out.append(v)
+    read = 0
+    for r in reads:
+        if read >= input_len or not r:
+            break
+        out += encode_block(_arr(r))
+        read += len(r)
+    return bytes(out), None
