@@ -50,6 +50,16 @@ __device__ unsigned long long g_stats[16];
 __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
+// x << n with PTX semantics: 0 once n >= 32 (C++ leaves that shift undefined)
+#ifdef SNB_EMULATE
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) { return n >= 32 ? 0u : x << n; }
+#else
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) {
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+  return r;
+}
+#endif
 // index of the lowest non-zero byte of x (x != 0)
 __device__ __forceinline__ uint32_t first_diff_byte(uint32_t x) { return (uint32_t)(__ffs((int)x) - 1) >> 3; }
 // Asynchronous 4-byte global -> shared copies (LDGSTS): completion is tracked per commit group, not by a
@@ -2196,14 +2206,13 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
       bad = avail < size;
     }
     if (bad) size = 64;
+    // J: the lane my tag's successor starts at; bit 5 set = beyond this step (sticky through the doubling below)
     uint32_t J = inb ? umin32(lane + size, 32) : 32;
     uint32_t R = 1u;
 #pragma unroll
     for (int r = 0; r < 4; r++) {  // 2^4 = 16 >= tags in 32 bytes (every element is >= 2 bytes)
-      uint32_t contrib = (((R >> lane) & 1u) && J < 32) ? (1u << J) : 0u;
-      R |= __reduce_or_sync(kFull, contrib);
-      uint32_t jn = __shfl_sync(kFull, J, (int)(J & 31));
-      J = J < 32 ? jn : 32;
+      R |= __reduce_or_sync(kFull, shl_clamp((R >> lane) & 1u, J));   // reached lanes mark their successor (none when J >= 32)
+      if (r < 3) J = __shfl_sync(kFull, J, (int)J) | (J & 32u);       // shfl takes the source lane modulo 32
     }
     const bool is_tag = inb && ((R >> lane) & 1u);
     const uint32_t val = (is_tag && !bad) ? L : 0;
