@@ -2105,8 +2105,28 @@ struct Chunk {
 // produced inside this step copy in parallel and the (few) dependent ones follow in order.
 // Accept/reject decisions equal the reference's for every input; only bytes past `written`
 // (scratch in the reference) are left untouched here.
+// Tag byte -> what decoder.nim:39-109 derives from it, as one shared-memory lookup (the branchy derivation is all
+// ALU-pipe work, the pipe this kernel saturates): x = L | size << 8 | offset high bits << 16, y = mask of the
+// offset bytes that follow the tag (0 for a literal).  Literals with a length field (tag >> 2 >= 60) have L = 0.
+__device__ __forceinline__ uint2 tag_entry(uint32_t t) {
+  const uint32_t kind = t & 3;
+  uint32_t L = (t >> 2) + 1, size, offhi = 0, mask = 0;
+  if (kind == 0) { size = 1 + L; if (L >= 61) { L = 0; size = 0; } }
+  else if (kind == 1) { L = 4 + ((t >> 2) & 7); size = 2; offhi = (t & 0xe0) << 3; mask = 0xffu; }
+  else if (kind == 2) { size = 3; mask = 0xffffu; }
+  else { size = 5; mask = 0xffffffffu; }
+  uint2 e;
+  e.x = L | (size << 8) | (offhi << 16);
+  e.y = mask;
+  return e;
+}
+__device__ __forceinline__ void stage_tag_lut(uint2* lut) {
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = tag_entry(i);
+  __syncthreads();
+}
+
 __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ in, uint32_t n, uint8_t* out,
-                                                   uint32_t cap, uint32_t* written, uint32_t lane) {
+                                                   uint32_t cap, uint32_t* written, uint32_t lane, const uint2* lut) {
   *written = 0;
   // ---- u32 varint (stew/leb128 via snappy.nim:92-94)
   uint32_t ulen = 0, br = 0;
@@ -2181,29 +2201,22 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     const bool inb = pos < tn;
     const uint32_t avail = inb ? tn - pos : 0;
     const uint32_t t = lo & 0xff, v4 = __funnelshift_r(lo, hi, 8);   // bytes past `avail` are never used when !bad
-    const uint32_t kind = t & 3;
     // ---- decode "a tag starting at my byte" (decoder.nim:39-109): L output bytes, `size` stream bytes
-    uint32_t L = (t >> 2) + 1, hdr = 1, off = 0, size;
-    bool bad;
-    if (kind == 0) {
-      size = 1 + L;
-      bad = avail < size;                                        // :77-79 (input side)
-      if (L >= 61) {                                             // :54-75
-        const uint32_t ll = L - 60;
-        bad = avail - 1 < 61;
-        const uint32_t m = ll == 4 ? 0xffffffffu : ((1u << (8 * ll)) - 1u);
-        L = (v4 & m) + 1;
-        if (L == 0) bad = true;
-        hdr = 1 + ll;
-        if (!bad && avail - hdr < L) bad = true;
-        size = hdr + L;
-      }
-    } else {
-      const bool k1 = kind == 1, k2 = kind == 2;
-      L = k1 ? 4 + ((t >> 2) & 7) : L;                           // :87-109
-      off = k1 ? (((t & 0xe0) << 3) | (v4 & 0xff)) : (k2 ? (v4 & 0xffff) : v4);
-      size = k1 ? 2u : (k2 ? 3u : 5u);
-      bad = avail < size;
+    const uint2 te = lut[t];
+    const bool lit = te.y == 0;
+    const uint32_t kind = lit ? 0u : 1u;                         // literal / copy is all the rest of the step needs
+    uint32_t L = te.x & 0xffu, size = (te.x >> 8) & 0xffu, hdr = 1;
+    const uint32_t off = (te.x >> 16) | (v4 & te.y);             // :87-109
+    bool bad = avail < size;                                     // :77-79 (input side)
+    if (L == 0) {                                                // literal with a length field, :54-75
+      const uint32_t ll = (t >> 2) - 59;
+      bad = avail - 1 < 61;
+      const uint32_t m = ll == 4 ? 0xffffffffu : ((1u << (8 * ll)) - 1u);
+      L = (v4 & m) + 1;
+      if (L == 0) bad = true;
+      hdr = 1 + ll;
+      if (!bad && avail - hdr < L) bad = true;
+      size = hdr + L;
     }
     if (bad) size = 64;
     // J: the lane my tag's successor starts at; bit 5 set = beyond this step (sticky through the doubling below)
@@ -2305,7 +2318,9 @@ struct DecompressArgs {
 constexpr uint32_t kDecThreads = SNB_DEC_THREADS, kDecBlocksPerSm = SNB_DEC_MINB;
 __global__ void __launch_bounds__(SNB_DEC_THREADS, SNB_DEC_MINB) decompress_kernel(DecompressArgs a, const CrcTables* g) {
   __shared__ CrcSmem t;
+  __shared__ uint2 lut[256];
   if (a.verify) crc_stage_tables(&t, g);
+  stage_tag_lut(lut);
   uint32_t lane = threadIdx.x & 31;
   for (;;) {
     uint32_t job = 0;
@@ -2319,7 +2334,7 @@ __global__ void __launch_bounds__(SNB_DEC_THREADS, SNB_DEC_MINB) decompress_kern
     uint32_t w = 0;
     const uint8_t* produced = out;
     if (c.kind == kKindCompressed) {
-      st = decompress_warp(in, c.in_len, out, c.out_cap, &w, lane);
+      st = decompress_warp(in, c.in_len, out, c.out_cap, &w, lane, lut);
     } else if (c.kind == kKindStored) {
       warp_copy(out, in, c.in_len, lane);
       w = c.in_len;
