@@ -143,6 +143,9 @@ void snb_set_profiling(int enabled);
 int snb_get_profile(float *ms, int n);
 /* Total kernels launched by this library since snb_init (for bench.py's gpu_launches). */
 uint64_t snb_kernel_launches(void);
+/* Raw streams of more than one block that snb_uncompress decoded block-parallel (block starts found on the device)
+ * rather than on a single warp -- for tests and tuning. */
+uint64_t snb_raw_block_decodes(void);
 /* Tuning: warps per CTA of the compress kernel for 64 KiB blocks (hash tables are 32 KiB each). */
 void snb_set_compress_warps(int warps);
 /* Tuning / A-B testing of the block encoder: 0 = auto (default: one thread per block with tables in HBM for

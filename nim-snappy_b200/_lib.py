@@ -58,6 +58,7 @@ SIGNATURES = {
     "snb_set_profiling": (None, [_i]),
     "snb_get_profile": (_i, [C.POINTER(C.c_float), _i]),
     "snb_kernel_launches": (_u64, []),
+    "snb_raw_block_decodes": (_u64, []),
     "snb_set_compress_warps": (None, [_i]),
     "snb_set_compress_algo": (None, [_i]),
     "snb_set_thread_min_chunks": (None, [_i]),

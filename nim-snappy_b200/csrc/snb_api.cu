@@ -24,6 +24,7 @@
 #define SNB_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(unsigned)(grid), (unsigned)(block), (size_t)(smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #endif
+#include <chrono>
 #include "snb_device.cuh"
 
 static_assert(sizeof(snb_chunk) == sizeof(snb::Chunk), "snb_chunk must match the device descriptor");
@@ -84,6 +85,8 @@ struct Ctx {
   DevBuf scratch, lens, offs, crcs, chunks, status, outlen, tables, in[4], out[4];
   PinBuf h_in[4], h_out[4], h_meta[4];
   DevBuf group_done, group_end;     // streaming compress: per-group placement counters / end offsets
+  uint64_t raw_block_decodes = 0;
+  DevBuf raw_in, raw_walk;          // raw multi-block discovery: the stream, and bitmap / per-segment / per-block tables
   PinBuf h_flags[2], h_arr;         // host-mapped group-complete flags per slab parity; arrival values per piece
   uint32_t* d_arrived = nullptr;    // chunks whose input has landed (streaming compress), then a timeout flag
   cudaEvent_t ev_reset = nullptr;
@@ -798,6 +801,82 @@ int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_
   return SNB_OK;
 }
 
+// A raw stream longer than one block (snappy.nim:84-110 over the output of :56-62): find the block starts on the
+// device (raw_walk_kernel / raw_validate_kernel, see snb_device.cuh), then decode the blocks as independent chunks.
+// *done = false means "not handled here" (not block structured, malformed, a copy reaching into an earlier block,
+// ...): the caller then runs the single-warp decoder, whose verdict is the reference's.
+int host_decode_raw_blocks(const uint8_t* in, size_t n, int br, uint64_t ulen, uint8_t* out, bool* done) {
+  *done = false;
+  if (ulen <= kChunk || (uint64_t)n > 0xffffffffull - (1u << 20) || (size_t)br >= n) return SNB_OK;
+  const uint64_t nblocks = (ulen + kChunk - 1) / kChunk;
+  uint32_t seg_shift = 10;                                   // about 8192 segments, 1 KiB .. 64 KiB of stream each
+  while (seg_shift < 16 && ((uint64_t)n >> seg_shift) > 8192) seg_shift++;
+  const uint32_t nseg = (uint32_t)(((uint64_t)n + (1u << seg_shift) - 1) >> seg_shift);
+  cudaStream_t st = g.s0;
+  CK(g.raw_in.ensure(n + 64));
+  CK(cudaMemcpyAsync(g.raw_in.p, in, n, cudaMemcpyHostToDevice, st));
+  // layout of raw_walk: flags[4] | bitmap | exitp | entry | exit2 | restart | block_start | outbytes (u64) | outbase (u64)
+  const size_t bm_words = n / 32 + 2;
+  const size_t off_bitmap = 4, off_exit = off_bitmap + bm_words, off_entry = off_exit + nseg, off_e2 = off_entry + nseg, off_rs = off_e2 + nseg, off_bs = off_rs + nseg;
+  size_t off_ob = off_bs + nblocks + 1;
+  off_ob = (off_ob + 1) & ~(size_t)1;                        // 8-byte alignment for the u64 tables
+  const size_t words = off_ob + 4 * (size_t)nseg;
+  CK(g.raw_walk.ensure(words * 4));
+  uint32_t* base = g.raw_walk.as<uint32_t>();
+  CK(cudaMemsetAsync(base, 0, (off_exit) * 4, st));                                  // flags + bitmap
+  CK(cudaMemsetAsync(base + off_bs, 0xff, (nblocks + 1) * 4, st));                   // block starts = kWalkNone
+  snb::RawWalkArgs a;
+  a.in = g.raw_in.as<uint8_t>(); a.n = (uint32_t)n; a.br = (uint32_t)br; a.seg_shift = seg_shift; a.nseg = nseg;
+  a.bitmap = base + off_bitmap; a.exitp = base + off_exit; a.entry = base + off_entry; a.exit2 = base + off_e2; a.restart = base + off_rs; a.block_start = base + off_bs;
+  a.outbytes = (unsigned long long*)(base + off_ob); a.outbase = a.outbytes + nseg; a.flags = base;
+  const uint32_t wpb = 8, grid = (nseg + wpb - 1) / wpb;
+  SNB_LAUNCH(snb::raw_walk_kernel<0>, grid, wpb * 32, 0, st, a); count_launch();
+  SNB_LAUNCH(snb::raw_walk_kernel<4>, grid, wpb * 32, 0, st, a); count_launch();
+  SNB_LAUNCH(snb::raw_validate_kernel, 1, 32, 0, st, a); count_launch();
+  SNB_LAUNCH(snb::raw_walk_kernel<1>, grid, wpb * 32, 0, st, a); count_launch();
+  CK(cudaGetLastError());
+  std::vector<unsigned long long> ob((size_t)nseg * 2);
+  uint32_t flags = 0;
+  CK(cudaMemcpyAsync(ob.data(), a.outbytes, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&flags, base, 4, cudaMemcpyDeviceToHost, st));
+  const auto t_a = std::chrono::steady_clock::now();
+  CK(cudaStreamSynchronize(st));
+  const auto t_b = std::chrono::steady_clock::now();
+  if (flags) return SNB_OK;
+  unsigned long long total = 0;
+  for (uint32_t s = 0; s < nseg; s++) { ob[nseg + s] = total; total += ob[s]; }
+  if (total != ulen) return SNB_OK;                          // snappy.nim:107-108 will say invalidInput
+  CK(cudaMemcpyAsync((void*)a.outbase, ob.data() + nseg, (size_t)nseg * 8, cudaMemcpyHostToDevice, st));
+  SNB_LAUNCH(snb::raw_walk_kernel<2>, grid, wpb * 32, 0, st, a); count_launch();
+  CK(cudaGetLastError());
+  std::vector<uint32_t> bs(nblocks + 1);
+  CK(cudaMemcpyAsync(bs.data(), a.block_start, nblocks * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&flags, base, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (flags) return SNB_OK;
+  bs[nblocks] = (uint32_t)n;
+  std::vector<snb_chunk> ch(nblocks);
+  for (uint64_t k = 0; k < nblocks; k++) {
+    if (bs[k] == snb::kWalkNone || bs[k + 1] == snb::kWalkNone || bs[k + 1] <= bs[k]) return SNB_OK;
+    ch[k].in_off = bs[k]; ch[k].in_len = bs[k + 1] - bs[k];
+    ch[k].out_off = k * kChunk; ch[k].out_cap = (uint32_t)std::min<uint64_t>(kChunk, ulen - k * kChunk);
+    ch[k].crc = 0; ch[k].kind = snb::kKindRawBlock;
+  }
+  int64_t bad = -1;
+  int32_t bad_status = 0;
+  const auto t_c = std::chrono::steady_clock::now();
+  CKS(host_decode_chunks(in, ch, out, 0, &bad, &bad_status));
+  if (getenv("SNB_DEBUG_RAW")) {
+    const auto t_d = std::chrono::steady_clock::now();
+    auto ms = [](auto x, auto y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
+    fprintf(stderr, "raw blocks: h2d+speculate+merge+validate+count %.2f ms, emit %.2f ms, decode %.2f ms (%u segments of %u B, %llu blocks)\n",
+            ms(t_a, t_b), ms(t_b, t_c), ms(t_c, t_d), nseg, 1u << seg_shift, (unsigned long long)nblocks);
+  }
+  *done = bad < 0;
+  if (*done) g.raw_block_decodes++;
+  return SNB_OK;
+}
+
 }  // namespace
 
 // ======================================================================== C ABI
@@ -912,6 +991,9 @@ int snb_uncompress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t
   if (br <= 0) return SNB_INVALID_INPUT;                                     // snappy.nim:92-94
   if ((uint64_t)cap < ulen) return SNB_BUFFER_TOO_SMALL;                     // :96-97
   ch[0].out_cap = (uint32_t)ulen;
+  bool done = false;
+  CKS(host_decode_raw_blocks(in, n, br, ulen, out, &done));                  // more than one block: block-parallel when possible
+  if (done) { *written = (size_t)ulen; return SNB_OK; }
   int64_t bad = -1;
   int32_t bad_status = 0;
   CKS(host_decode_chunks(in, ch, out, 0, &bad, &bad_status));
@@ -1101,6 +1183,7 @@ int snb_get_profile(float* ms, int n) {
   return k;
 }
 uint64_t snb_kernel_launches(void) { return g.launches; }
+uint64_t snb_raw_block_decodes(void) { return g.raw_block_decodes; }
 void snb_set_compress_warps(int warps) { g.compress_warps = warps % 100; if (warps >= 100) g.compress_gwarps = warps / 100 - 1; }
 void snb_set_compress_algo(int algo) { g.compress_algo = algo; }
 void snb_set_thread_min_chunks(int n) { g.thread_min_chunks = n; }

@@ -35,7 +35,7 @@ constexpr uint32_t kMaxDeviceMessage = 1u << 28;  // per-message bound of the wa
 
 enum : int32_t { kOk = 0, kBufferTooSmall = 1, kInvalidInput = 2, kCrcMismatch = 3, kUnknownChunk = 4, kUnsupported = 101 };
 enum : uint32_t { kModeFrame = 0, kModeRawBlock = 1, kModeRawMessage = 2 };
-enum : uint32_t { kKindCompressed = 0, kKindStored = 1, kKindVerifyOnly = 2 };
+enum : uint32_t { kKindCompressed = 0, kKindStored = 1, kKindVerifyOnly = 2, kKindRawBlock = 3 };  // 3: bare tags of one block, out_cap = its exact length
 
 // Optional event counters for tuning (tests/emu builds with -DSNB_STATS; never in the product build).
 #ifdef SNB_STATS
@@ -2126,11 +2126,13 @@ __device__ __forceinline__ void stage_tag_lut(uint2* lut) {
 }
 
 __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ in, uint32_t n, uint8_t* out,
-                                                   uint32_t cap, uint32_t* written, uint32_t lane, const uint2* lut) {
+                                                   uint32_t cap, uint32_t* written, uint32_t lane, const uint2* lut,
+                                                   bool bare = false) {
   *written = 0;
-  // ---- u32 varint (stew/leb128 via snappy.nim:92-94)
-  uint32_t ulen = 0, br = 0;
-  {
+  // ---- u32 varint (stew/leb128 via snappy.nim:92-94); a bare block (one 64 KiB block of a longer raw stream,
+  // found by the discovery pass below) has no length prefix: it must produce exactly `cap` bytes
+  uint32_t ulen = bare ? cap : 0, br = 0;
+  if (!bare) {
     bool done = false, bad = false;
     for (uint32_t i = 0; i < 5 && !done && !bad; i++) {
       if (i >= n) { bad = true; break; }
@@ -2335,6 +2337,8 @@ __global__ void __launch_bounds__(SNB_DEC_THREADS, SNB_DEC_MINB) decompress_kern
     const uint8_t* produced = out;
     if (c.kind == kKindCompressed) {
       st = decompress_warp(in, c.in_len, out, c.out_cap, &w, lane, lut);
+    } else if (c.kind == kKindRawBlock) {
+      st = decompress_warp(in, c.in_len, out, c.out_cap, &w, lane, lut, true);
     } else if (c.kind == kKindStored) {
       warp_copy(out, in, c.in_len, lane);
       w = c.in_len;
@@ -2377,6 +2381,187 @@ __global__ void varint_lens_kernel(const uint8_t* base, const uint64_t* in_off, 
     if (!(b & 0x80)) { done = true; break; }
   }
   lens[i] = done ? v : 0xffffffffu;
+}
+
+// ===================================================================== raw streams longer than one block
+// The raw format (snappy.nim:27-64) is Leb128(len) followed by the tags of consecutive 64 KiB blocks, with nothing
+// marking where a block's tags start.  Encoders of this family (the reference, C++ snappy) compress every block
+// on its own, so once the block starts are known the blocks decode independently, one warp each.  Finding them is
+// a walk over the tag chain; it is made parallel by speculation:
+//
+//   speculate  one warp per segment of the stream walks tags from the segment's first byte as if a tag started
+//              there, marking every position it visits in a bitmap and noting where it leaves the segment.  A
+//              tag that cannot be (it overruns the stream) makes the walk start over at the next byte; a chain
+//              that meets a position visited BEFORE the last such restart runs into that impossible tag.
+//   merge      a tag chain started at a wrong byte falls into step with the true one after a few tags.  Every
+//              segment is walked from the previous segment's speculative exit -- its true entry if that
+//              segment was itself on the chain -- until it meets a position its own speculative walk visited:
+//              from there on the two coincide, so the speculative exit is the exit for that entry.
+//   validate   one warp follows the true chain across segments, taking each segment's exit from the merge
+//              pass when its true entry is the assumed one (nearly always) and re-walking it otherwise
+//              (after a literal that jumped over whole segments).
+//   count      every segment is walked again from its true entry, summing the output bytes of its tags.
+//   emit       with the prefix sums of those counts, the same walk writes down the stream position of every
+//              tag whose output offset is a multiple of 65536, and flags elements that straddle a boundary.
+//
+// The walk applies exactly the decoder's rules for tag sizes and truncation (decoder.nim:39-109).  Anything
+// unusual -- a malformed chain, a total that is not the announced length, an element crossing a block boundary,
+// a copy reaching back into an earlier block (caught by the block decoder) -- sends the whole stream to the
+// single-warp decoder, whose verdict is the reference's.
+constexpr uint32_t kWalkNone = 0xffffffffu, kWalkBad = 0xfffffffeu;
+struct RawWalkArgs {
+  const uint8_t* in;                  // the whole raw stream, length prefix included
+  uint32_t n, br;                     // its size; bytes of the length prefix
+  uint32_t seg_shift, nseg;           // segment s = stream bytes [s << seg_shift, (s + 1) << seg_shift)
+  uint32_t* bitmap;                   // speculate: visited positions (zeroed, n / 32 + 2 words)
+  uint32_t* exitp;                    // speculate: per segment, first visited position past the segment, or kWalkBad
+  uint32_t* restart;                  // speculate: per segment, where the walk last had to start over (0: never)
+  uint32_t* exit2;                    // merge: per segment, the exit when entered at the previous segment's exitp
+  uint32_t* entry;                    // validate: per segment, true first tag in it, or kWalkNone
+  unsigned long long* outbytes;       // count: per segment
+  const unsigned long long* outbase;  // emit: exclusive prefix sums of outbytes
+  uint32_t* block_start;              // emit: per block (preset to kWalkNone)
+  uint32_t* flags;                    // [0]: 1 = chain malformed / does not end at n, 2 = not block structured
+};
+
+// kMode 0 speculate, 1 count, 2 emit, 3 / 4 walk from `start` until the speculative chain is met (validate's repair /
+// the merge pass).  Uniform return value: the first chain position at or past the segment end, or kWalkBad.
+template <int kMode>
+__device__ __forceinline__ uint32_t raw_walk_warp(const RawWalkArgs& a, uint32_t s, uint32_t start, const uint2* lut,
+                                                  uint32_t lane) {
+  const uint32_t n = a.n;
+  const uint32_t seg_hi = umin32(n, (s + 1) << a.seg_shift);
+  const uint32_t mis = (uint32_t)((uintptr_t)a.in & 3);
+  const uint32_t* const w = (const uint32_t*)(a.in - mis);
+  const uint32_t wlast = (n + mis - 1) >> 2;
+  uint32_t ip = start;
+  uint32_t rs = 0;   // speculate: start of the current chain fragment
+  unsigned long long o = kMode == 2 ? a.outbase[s] : 0ull;
+  while (ip < seg_hi) {
+    const uint32_t pos = ip + lane;
+    const bool inb = pos < n;
+    const uint32_t avail = inb ? n - pos : 0;
+    const uint32_t i = pos + mis, k = i >> 2, sh = (i & 3) * 8;
+    const uint32_t w0 = __ldg(w + umin32(k, wlast)), w1 = __ldg(w + umin32(k + 1, wlast)), w2 = __ldg(w + umin32(k + 2, wlast));
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    const uint32_t t = lo & 0xff, v4 = __funnelshift_r(lo, hi, 8);
+    const uint2 te = lut[t];
+    uint32_t L = te.x & 0xffu, size = (te.x >> 8) & 0xffu;
+    bool bad = avail < size;
+    if (L == 0) {  // literal with a length field, decoder.nim:54-75
+      const uint32_t ll = (t >> 2) - 59;
+      bad = avail - 1 < 61;
+      const uint32_t m = ll == 4 ? 0xffffffffu : ((1u << (8 * ll)) - 1u);
+      L = (v4 & m) + 1;
+      if (L == 0) bad = true;
+      if (!bad && avail - (1 + ll) < L) bad = true;
+      size = 1 + ll + L;
+    }
+    if (bad) size = 64;
+    uint32_t J = inb ? umin32(lane + size, 32) : 32;
+    uint32_t R = 1u;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      R |= __reduce_or_sync(kFull, shl_clamp((R >> lane) & 1u, J));
+      if (r < 3) J = __shfl_sync(kFull, J, (int)J) | (J & 32u);
+    }
+    const bool is_tag = inb && ((R >> lane) & 1u);
+    const bool mine = is_tag && pos < seg_hi;         // tags at or past the segment end belong to the next segment
+    const uint32_t badm = __ballot_sync(kFull, mine && bad);
+    if (kMode != 0 && badm) return kWalkBad;
+    if (kMode == 3 || kMode == 4) {  // met a position the speculative walk of this segment visited: same chain from here on
+      const uint32_t m = __ballot_sync(kFull, mine);
+      const uint32_t bw = __funnelshift_r(a.bitmap[ip >> 5], a.bitmap[(ip >> 5) + 1], ip & 31u);
+      if (m & bw) return ip + (uint32_t)__ffs((int)(m & bw)) - 1u >= a.restart[s] ? a.exitp[s] : kWalkBad;
+    }
+    if (kMode == 0) {
+      const uint32_t m = __ballot_sync(kFull, mine);
+      if (lane == 0) {
+        atomicOr(a.bitmap + (ip >> 5), m << (ip & 31u));
+        if (ip & 31u) atomicOr(a.bitmap + (ip >> 5) + 1, m >> (32u - (ip & 31u)));
+      }
+      if (badm) {  // not a tag chain after all: any byte is as good a guess as the first one was
+        ip = ip + (uint32_t)__ffs((int)badm);
+        rs = ip;
+        continue;
+      }
+    }
+    if (kMode == 1 || kMode == 2) {
+      const uint32_t val = mine ? L : 0u;
+      uint32_t incl = val;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(kFull, incl, d);
+        if (lane >= (uint32_t)d) incl += u;
+      }
+      if (kMode == 2 && mine) {
+        const unsigned long long my_o = o + (incl - val);
+        if ((my_o & 0xffffull) == 0) a.block_start[my_o >> 16] = pos;
+        if ((my_o >> 16) != ((my_o + L - 1) >> 16)) atomicOr(a.flags, 2u);
+      }
+      o += __shfl_sync(kFull, incl, 31);
+    }
+    const uint32_t over = __ballot_sync(kFull, is_tag && pos >= seg_hi);
+    if (over) { ip = ip + (uint32_t)__ffs((int)over) - 1u; break; }
+    const uint32_t tagmask = __ballot_sync(kFull, is_tag);
+    ip = __shfl_sync(kFull, pos + size, 31 - __clz((int)tagmask));   // the last tag of the step is not bad (checked above)
+  }
+  if (kMode == 1 && lane == 0) a.outbytes[s] = o;
+  if (kMode == 0 && lane == 0) a.restart[s] = rs;
+  return ip;
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(256) raw_walk_kernel(RawWalkArgs a) {
+  __shared__ uint2 lut[256];
+  stage_tag_lut(lut);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= a.nseg) return;
+  uint32_t start;
+  if (kMode == 0) start = s == 0 ? a.br : (s << a.seg_shift);
+  else if (kMode == 4) {
+    start = s == 0 ? a.br : a.exitp[s - 1];
+    if (start >= umin32(a.n, (s + 1) << a.seg_shift)) start = kWalkNone;   // bad, or beyond this segment
+  } else start = a.entry[s];
+  if (start == kWalkNone) {  // the chain jumps over this segment (a long literal)
+    if (kMode == 1 && lane == 0) a.outbytes[s] = 0;
+    if (kMode == 4 && lane == 0) a.exit2[s] = kWalkNone;
+    return;
+  }
+  const uint32_t e = raw_walk_warp<kMode>(a, s, start, lut, lane);
+  if (kMode == 0 && lane == 0) a.exitp[s] = e;
+  if (kMode == 4 && lane == 0) a.exit2[s] = e;
+  if ((kMode == 1 || kMode == 2) && e == kWalkBad && lane == 0) atomicOr(a.flags, 1u);
+}
+
+// One warp: the true chain across segments (see above).  32 segments per turn: the merge pass's exits are fetched
+// by all lanes at once, the dependent part runs on shuffles.
+__global__ void __launch_bounds__(32) raw_validate_kernel(RawWalkArgs a) {
+  __shared__ uint2 lut[256];
+  stage_tag_lut(lut);
+  const uint32_t lane = threadIdx.x;
+  uint32_t X = a.br;   // the next true tag position
+  bool dead = false;
+  for (uint32_t s0 = 0; s0 < a.nseg; s0 += 32) {
+    const uint32_t sj = s0 + lane;
+    const uint32_t e2 = sj < a.nseg ? a.exit2[sj] : kWalkNone;
+    const uint32_t as = sj == 0 ? a.br : (sj < a.nseg ? a.exitp[sj - 1] : kWalkNone);   // the entry the merge pass assumed
+    uint32_t my_entry = kWalkNone;
+    for (uint32_t j = 0; j < 32 && s0 + j < a.nseg; j++) {
+      const uint32_t s = s0 + j;
+      const uint32_t seg_hi = umin32(a.n, (s + 1) << a.seg_shift);
+      if (dead || X >= seg_hi) continue;
+      uint32_t ej = __shfl_sync(kFull, e2, (int)j);
+      const uint32_t aj = __shfl_sync(kFull, as, (int)j);
+      if (aj != X) ej = raw_walk_warp<3>(a, s, X, lut, lane);   // entered somewhere else than assumed (after a jump)
+      if (lane == j) my_entry = X;
+      if (ej == kWalkBad) { dead = true; continue; }
+      X = ej;
+    }
+    if (sj < a.nseg) a.entry[sj] = my_entry;
+  }
+  if (lane == 0 && (dead || X != a.n)) atomicOr(a.flags, 1u);
 }
 
 }  // namespace snb

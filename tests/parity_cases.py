@@ -252,3 +252,53 @@ def check_faststreams_errors(fs, o):
             got = _fs_decode(fs, s, ci)
             assert got == want, (i, ci, got[1], want[1], len(got[0]), len(want[0]))
         assert _fs_decode(fs, s, source=_NoLenReader(s, 7)) == o.fs_uncompress_framed(s, True), i
+
+
+# ---------------------------------------------------------------- raw streams longer than one block
+def _varint(v):
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7f) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def _lit(b):
+    """One literal element holding b (decoder.nim:39-79 encodings)."""
+    n = len(b) - 1
+    if n < 60:
+        return bytes([n << 2]) + b
+    k = (n.bit_length() + 7) // 8
+    return bytes([(59 + k) << 2]) + n.to_bytes(k, "little") + b
+
+
+def check_raw_multiblock(api, o, cpp, datas, fuzz=6):
+    """`uncompress` of raw streams of several blocks: the block-discovery path (raw_walk_kernel) and its fall-backs
+    give the oracle's bytes and statuses."""
+    rng = np.random.default_rng(5)
+    for d in datas:
+        enc = o.encode(d)
+        n0 = api.lib.snb_raw_block_decodes()
+        assert api.decode(enc) == d                                   # reference-encoded, block structured
+        if cpp is not None:
+            assert api.decode(cpp.encode(d)) == d                     # C++ snappy blocks (tests/test_snappy.nim:68)
+        assert api.lib.snb_raw_block_decodes() - n0 == (2 if cpp is not None else 1)   # ... and decoded block-parallel
+        for s in (enc[:-1], enc[:len(enc) // 2], enc + b"\x00", _varint(len(d) + 1) + enc[len(_varint(len(d))):],
+                  _varint(len(d) - 1) + enc[len(_varint(len(d))):]):
+            check_raw_decode_parity(api, o, s)                        # truncated / trailing / wrong announced length
+        for s in mutate_streams(o, enc, rng, fuzz):
+            check_raw_decode_parity(api, o, s)
+    # streams no block-wise encoder would write, all valid: they must take the single-warp route and still decode
+    a = bytes(rng.integers(0, 256, 65536, dtype=np.uint8))
+    b = bytes(rng.integers(0, 7, 3000, dtype=np.uint8))
+    straddle = _varint(65536 + 3000) + _lit(a[:65000]) + _lit(a[65000:] + b)            # an element across the 64 KiB line
+    n0 = api.lib.snb_raw_block_decodes()
+    assert o.decode(straddle) == a + b and api.decode(straddle) == a + b
+    back = _varint(65536 + 64 + 10) + _lit(a) + bytes([(63 << 2) | 3]) + (65536).to_bytes(4, "little") + _lit(b[:10])
+    assert o.decode(back) == a + a[:64] + b[:10] and api.decode(back) == a + a[:64] + b[:10]   # copy4 into the previous block
+    near = _varint(65536 + 64) + _lit(a) + bytes([(63 << 2) | 2]) + (65535).to_bytes(2, "little")
+    assert o.decode(near) == a + a[1:65] and api.decode(near) == a + a[1:65]                   # copy2 across the line
+    far = _varint(65536 + 64) + _lit(a) + bytes([(63 << 2) | 3]) + (65537).to_bytes(4, "little")
+    check_raw_decode_parity(api, o, far)                                                         # offset beyond the start
+    assert api.lib.snb_raw_block_decodes() == n0

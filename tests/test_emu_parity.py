@@ -98,3 +98,11 @@ def test_every_block_encoder_variant(emu_api, oracle, algo):
             P.check_raw(emu_api, oracle, bytes(n))
     finally:
         lib.snb_set_compress_algo(0)
+
+
+def test_raw_multiblock(emu_api, oracle):
+    rng = np.random.default_rng(9)
+    alice = read_data("alice29.txt")
+    P.check_raw_multiblock(emu_api, oracle, oracle.ref_snappycpp(),
+                           [alice[:140000], rng.integers(0, 256, 135000, dtype=np.uint8).tobytes(),
+                            alice[:66000] + rng.integers(0, 256, 70000, dtype=np.uint8).tobytes() + alice[:3000]], fuzz=3)

@@ -125,7 +125,31 @@ def test_raw_multiblock_and_big(gpu_api, oracle):
     d = read_data("plrabn12.txt") + read_data("kppkn.gtb")
     P.check_raw(gpu_api, oracle, d)
     big = np.tile(np.frombuffer(read_data("lcet10.txt"), dtype=np.uint8), 170)[: 70 << 20].tobytes()  # > 1 host slab
-    assert gpu_api.encode(big) == oracle.encode(big)
+    enc = oracle.encode(big)
+    assert gpu_api.encode(big) == enc
+    n0 = gpu_api.lib.snb_raw_block_decodes()
+    assert gpu_api.decode(enc) == big                      # 1 120 blocks, found on the device and decoded in parallel
+    assert gpu_api.lib.snb_raw_block_decodes() == n0 + 1
+
+
+def test_raw_multiblock_decode(gpu_api, oracle):
+    """block discovery + block-parallel decode of long raw streams, and the streams that must not take it."""
+    import time
+    from nim_snappy_b200.workloads import mixed_corpus, text_corpus
+    rng = np.random.default_rng(4)
+    P.check_raw_multiblock(gpu_api, oracle, oracle.ref_snappycpp(),
+                           [read_data("lcet10.txt"), read_data("urls.10K"), read_data("fireworks.jpeg"),
+                            read_data("alice29.txt") + rng.integers(0, 256, 300000, dtype=np.uint8).tobytes() + read_data("html")])
+    for d in (text_corpus(300 << 20), mixed_corpus(300 << 20, seed=2)):     # beyond the 256 MiB single-warp bound
+        enc = oracle.encode(d)
+        out = np.empty(d.size, dtype=np.uint8)
+        n0 = gpu_api.lib.snb_raw_block_decodes()
+        t0 = time.perf_counter()
+        r = gpu_api.uncompress(enc, out)
+        dt = time.perf_counter() - t0
+        assert r == d.size and bool((out == d).all())
+        assert gpu_api.lib.snb_raw_block_decodes() == n0 + 1
+        print(f"raw uncompress of {d.size >> 20} MiB through host buffers: {d.size / dt / 1e9:.1f} GB/s")
 
 
 def test_host_api_multi_slab_and_pinned(gpu_api, oracle):
