@@ -809,8 +809,10 @@ int host_decode_raw_blocks(const uint8_t* in, size_t n, int br, uint64_t ulen, u
   *done = false;
   if (ulen <= kChunk || (uint64_t)n > 0xffffffffull - (1u << 20) || (size_t)br >= n) return SNB_OK;
   const uint64_t nblocks = (ulen + kChunk - 1) / kChunk;
-  uint32_t seg_shift = 10;                                   // about 8192 segments, 1 KiB .. 64 KiB of stream each
-  while (seg_shift < 16 && ((uint64_t)n >> seg_shift) > 8192) seg_shift++;
+  // Small segments: when a speculative walk never meets the true chain (it left its segment through a fake long
+  // literal inside incompressible bytes) the validating warp re-walks that segment on its own, serially.
+  uint32_t seg_shift = 10;                                   // 1 KiB .. 4 KiB of stream per segment (more beyond 1 GiB)
+  while (seg_shift < 16 && ((uint64_t)n >> seg_shift) > (seg_shift < 12 ? 8192u : 262144u)) seg_shift++;
   const uint32_t nseg = (uint32_t)(((uint64_t)n + (1u << seg_shift) - 1) >> seg_shift);
   cudaStream_t st = g.s0;
   CK(g.raw_in.ensure(n + 64));
@@ -830,11 +832,29 @@ int host_decode_raw_blocks(const uint8_t* in, size_t n, int br, uint64_t ulen, u
   a.bitmap = base + off_bitmap; a.exitp = base + off_exit; a.entry = base + off_entry; a.exit2 = base + off_e2; a.restart = base + off_rs; a.block_start = base + off_bs;
   a.outbytes = (unsigned long long*)(base + off_ob); a.outbase = a.outbytes + nseg; a.flags = base;
   const uint32_t wpb = 8, grid = (nseg + wpb - 1) / wpb;
+  const bool dbg = getenv("SNB_DEBUG_RAW") != nullptr;
+  cudaEvent_t ev[5] = {};
+  if (dbg) for (auto& e : ev) cudaEventCreate(&e);
+  if (dbg) cudaEventRecord(ev[0], st);
   SNB_LAUNCH(snb::raw_walk_kernel<0>, grid, wpb * 32, 0, st, a); count_launch();
+  if (dbg) cudaEventRecord(ev[1], st);
   SNB_LAUNCH(snb::raw_walk_kernel<4>, grid, wpb * 32, 0, st, a); count_launch();
+  if (dbg) cudaEventRecord(ev[2], st);
   SNB_LAUNCH(snb::raw_validate_kernel, 1, 32, 0, st, a); count_launch();
+  if (dbg) cudaEventRecord(ev[3], st);
   SNB_LAUNCH(snb::raw_walk_kernel<1>, grid, wpb * 32, 0, st, a); count_launch();
+  if (dbg) cudaEventRecord(ev[4], st);
   CK(cudaGetLastError());
+  if (dbg) {
+    cudaEventSynchronize(ev[4]);
+    float t[4];
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+    uint32_t f4[4] = {};
+    cudaMemcpy(f4, base, 16, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "raw blocks: speculate %.2f ms, merge %.2f ms, validate %.2f ms (%u re-walks, %.2f ms, %u over 0.1 ms), count %.2f ms\n", t[0], t[1], t[2],
+            f4[1], f4[2] * 1e-6, f4[3], t[3]);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   std::vector<unsigned long long> ob((size_t)nseg * 2);
   uint32_t flags = 0;
   CK(cudaMemcpyAsync(ob.data(), a.outbytes, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st));

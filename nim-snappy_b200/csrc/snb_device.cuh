@@ -2547,14 +2547,34 @@ __global__ void __launch_bounds__(32) raw_validate_kernel(RawWalkArgs a) {
     const uint32_t sj = s0 + lane;
     const uint32_t e2 = sj < a.nseg ? a.exit2[sj] : kWalkNone;
     const uint32_t as = sj == 0 ? a.br : (sj < a.nseg ? a.exitp[sj - 1] : kWalkNone);   // the entry the merge pass assumed
+    {  // the regular case, all 32 at once: every segment is entered where the merge pass assumed and left inside the next one
+      uint32_t px = __shfl_up_sync(kFull, e2, 1);
+      if (lane == 0) px = X;
+      const bool in_range = sj < a.nseg;
+      const bool reg = !in_range || (px == as && px < umin32(a.n, (sj + 1) << a.seg_shift) && e2 < kWalkBad);
+      if (!dead && __all_sync(kFull, reg)) {
+        if (in_range) a.entry[sj] = px;
+        X = __shfl_sync(kFull, e2, (int)(umin32(a.nseg - s0, 32u) - 1u));
+        continue;
+      }
+    }
     uint32_t my_entry = kWalkNone;
+#pragma unroll 1   // one copy of the re-walk: a lone warp running through 32 unrolled copies lives on instruction-cache misses
     for (uint32_t j = 0; j < 32 && s0 + j < a.nseg; j++) {
       const uint32_t s = s0 + j;
       const uint32_t seg_hi = umin32(a.n, (s + 1) << a.seg_shift);
       if (dead || X >= seg_hi) continue;
       uint32_t ej = __shfl_sync(kFull, e2, (int)j);
       const uint32_t aj = __shfl_sync(kFull, as, (int)j);
-      if (aj != X) ej = raw_walk_warp<3>(a, s, X, lut, lane);   // entered somewhere else than assumed (after a jump)
+      if (aj != X) {   // entered somewhere else than assumed (after a jump)
+        const unsigned long long t0 = snb_now_ns();
+        ej = raw_walk_warp<3>(a, s, X, lut, lane);
+        if (lane == 0) {   // statistics: re-walks, their time, the long ones
+          const uint32_t dt = (uint32_t)(snb_now_ns() - t0);
+          a.flags[1]++; a.flags[2] += dt;
+          if (dt > 100000u) a.flags[3]++;
+        }
+      }
       if (lane == j) my_entry = X;
       if (ej == kWalkBad) { dead = true; continue; }
       X = ej;
