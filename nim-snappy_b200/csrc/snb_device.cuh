@@ -1755,6 +1755,14 @@ __global__ void __launch_bounds__(kStreamMaxThreads, 1) compress_stream_kernel(S
   }
 }
 
+// Keeps one thread busy for `ns` nanoseconds: the host times the launch CALL of this kernel to find out whether
+// launches block (profilers, CUDA_LAUNCH_BLOCKING); a kernel that waits for copies enqueued after it must not be
+// launched before them then.
+__global__ void launch_probe_kernel(unsigned ns) {
+  const unsigned long long t0 = snb_now_ns();
+  while (snb_now_ns() - t0 < ns) snb_sleep(1000);
+}
+
 // frontier = (base << 24) for the first slab, or continues at *prev_total.
 __global__ void stream_init_kernel(unsigned long long* frontier, const unsigned long long* prev_total,
                                    unsigned long long base, unsigned long long* total) {
