@@ -1596,6 +1596,21 @@ __device__ __forceinline__ unsigned long long snb_now_ns() {
 __device__ __forceinline__ void snb_sleep(unsigned ns) { __nanosleep(ns); }
 __device__ __forceinline__ uint32_t ld_cg32(const uint32_t* p) { return __ldcg(p); }
 #endif
+// Release operations at GPU scope.  Unlike __threadfence() (MEMBAR.SC.GPU + CCTL.IVALL in SASS) they do not
+// invalidate the SM's L1, which the 22 encoder warps of the CTA live on (candidate loads): MEMBAR.ALL.GPU only.
+#ifdef SNB_EMULATE
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { *p = v; }
+__device__ __forceinline__ uint32_t atom_add_release_gpu(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+#else
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_release_gpu(uint32_t* p, uint32_t v) {
+  uint32_t o;
+  asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+  return o;
+}
+#endif
 
 // Copy n bytes, any alignment, reading through L2 only (the source was written by another SM).
 __device__ __forceinline__ void warp_copy_cg(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) {
@@ -1689,8 +1704,7 @@ __device__ __forceinline__ void stream_place(const StreamArgs& a, uint32_t lane)
         const bool last_of_group = ci + 1 == gfirst + gsize;
         if (last_of_group) *(volatile unsigned long long*)(a.group_end + grp) = off + clen;
         if (ci + 1 == count) *(volatile unsigned long long*)a.total = off + clen;
-        __threadfence();
-        if (atomicAdd(a.group_done + grp, 1u) + 1 == gsize && a.host_flags) {
+        if (atom_add_release_gpu(a.group_done + grp, 1u) + 1 == gsize && a.host_flags) {   // the chunk's bytes before the count
           __threadfence();
           const unsigned long long end = *(volatile unsigned long long*)(a.group_end + grp);
           __threadfence_system();
@@ -1745,9 +1759,8 @@ __global__ void __launch_bounds__(kStreamMaxThreads, 1) compress_stream_kernel(S
     const uint32_t total = compress_job<5>(a.c, job, table, lane, 0, tglobal, crc, false);
     __syncwarp();
     if (lane == 0) {
-      __threadfence();   // the frame's bytes before its length
-      *(volatile uint32_t*)(a.c.out_len + job) = total;
-      __threadfence();   // ... and the length before this warp looks at the frontier
+      st_release_gpu(a.c.out_len + job, total);   // the frame's bytes before its length
+      __threadfence();   // ... and the length before this warp looks at the frontier (store -> load: needs the full fence)
     }
     __syncwarp();
     stream_place(a, lane);
