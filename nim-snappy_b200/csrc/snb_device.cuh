@@ -1533,7 +1533,7 @@ __global__ void __launch_bounds__(kCompressMaxThreads, 1) compress_kernel(Compre
 
 // The v5 encoder on its own register budget (no staging area: the tables are the only shared memory).
 #ifndef SNB_COMPRESS5_MAXT
-#define SNB_COMPRESS5_MAXT 768
+#define SNB_COMPRESS5_MAXT 704
 #endif
 constexpr uint32_t kCompress5MaxThreads = SNB_COMPRESS5_MAXT;
 __global__ void __launch_bounds__(kCompress5MaxThreads, 1) compress_kernel5(CompressArgs a) {
@@ -1716,8 +1716,11 @@ __device__ __forceinline__ void stream_place(const StreamArgs& a, uint32_t lane)
   }
 }
 
+// 22 warps (4 shared-memory + 18 L2 tables) is the measured optimum, so the kernel is compiled for exactly that:
+// with a bound of 704 threads ptxas produces a schedule (same 80 registers, no spills) that runs 8 % faster than the
+// one for 768 (text 42.6 -> 46.2 GB/s, mixed 61.8 -> 66.8); 672 spills and drops to 35 GB/s.
 #ifndef SNB_STREAM_MAXT
-#define SNB_STREAM_MAXT 768
+#define SNB_STREAM_MAXT 704
 #endif
 constexpr uint32_t kStreamMaxThreads = SNB_STREAM_MAXT;
 constexpr unsigned long long kArriveTimeoutNs = 20ull * 1000 * 1000 * 1000;
