@@ -1,4 +1,4 @@
-# round-1g: tests, bench, launch list and full ncu captures of the two hot kernels (compress also with warm caches)
+# round-1h: tests, bench, launch list and full ncu captures of the two hot kernels (compress also with warm caches)
 set -x
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
