@@ -85,7 +85,9 @@ __device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 #endif
+#ifndef SNB_V5_HINT
 #define SNB_V5_HINT 1   // 0: none, 1: L1 hint, 2: L2 hint for the next window's candidates
+#endif
 // Unaligned little-endian 32-bit load built from aligned words.  Only words holding at least
 // one requested byte are touched.
 __device__ __forceinline__ uint32_t load32u(const uint8_t* p) {
