@@ -544,6 +544,8 @@ int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, ui
     *pos += total;
     return SNB_OK;
   }
+  const bool dbg_e2e = getenv("SNB_DEBUG_E2E") != nullptr;   // host-side timeline of the streaming pipeline on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
   const uint64_t slab_bytes = (uint64_t)kDevSlabChunks * kChunk;
   const uint64_t nslab = (n + slab_bytes - 1) / slab_bytes;
   const uint64_t piece_bytes = (uint64_t)kGroupChunks * kChunk;
@@ -621,6 +623,8 @@ int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, ui
     unsigned long long prev = 0, end = 0;
     for (uint64_t gi = 0; gi < groups; gi++) {
       CKS(wait_group_flag(flags + gi, g.ev_comp[s], &end));
+      if (dbg_e2e) fprintf(stderr, "  slab %llu group %llu packed at %.2f ms (%llu bytes so far)\n", (unsigned long long)k,
+                           (unsigned long long)gi, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), end);
       if (end > prev) CK(cudaMemcpyAsync(out + *pos + prev, g.out[s].as<uint8_t>() + prev, end - prev, cudaMemcpyDeviceToHost, g.s_out));
       prev = end;
     }
@@ -629,6 +633,7 @@ int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, ui
     return SNB_OK;
   };
   CKS(enqueue(0));
+  if (dbg_e2e) fprintf(stderr, "host_compress: slab 0 enqueued at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
   for (uint64_t k = 0; k < nslab; k++) {
     if (k + 1 < nslab) CKS(enqueue(k + 1));
     CKS(drain(k));
@@ -637,6 +642,7 @@ int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, ui
   CK(cudaStreamSynchronize(g.s_in));
   CK(cudaStreamSynchronize(g.s0));
   CK(cudaStreamSynchronize(g.s_out));
+  if (dbg_e2e) fprintf(stderr, "host_compress: all streams drained at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
   if (*g.h_meta[0].as<uint32_t>() != 0) { g.err = "streaming compress: timed out waiting for input pieces"; return SNB_CUDA_ERROR; }
   return SNB_OK;
 }
