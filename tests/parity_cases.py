@@ -302,3 +302,40 @@ def check_raw_multiblock(api, o, cpp, datas, fuzz=6):
     far = _varint(65536 + 64) + _lit(a) + bytes([(63 << 2) | 3]) + (65537).to_bytes(4, "little")
     check_raw_decode_parity(api, o, far)                                                         # offset beyond the start
     assert api.lib.snb_raw_block_decodes() == n0
+
+
+def random_element_stream(rng, target, max_lit=3000, far=True):
+    """A VALID raw stream assembled from random elements (decoder.nim:39-151 encodings), not from an encoder: literals of
+    any length, copy1 / copy2 / copy4 with arbitrary in-range offsets -- elements straddle 64 KiB lines and copies reach
+    across them at random, which no block-wise encoder does."""
+    out = bytearray()
+    op = 0
+    while op < target:
+        kind = int(rng.integers(0, 4)) if op >= 4 else 0
+        if kind == 0:
+            n = int(rng.integers(1, max_lit)) if rng.random() < 0.9 else int(rng.integers(60000, 70000))
+            out += _lit(bytes(rng.integers(0, 256, n, dtype=np.uint8)))
+            op += n
+        elif kind == 1:
+            off = int(rng.integers(1, min(op, 2047) + 1)); ln = int(rng.integers(4, 12))
+            out += bytes([((off >> 8) << 5) | ((ln - 4) << 2) | 1, off & 0xff]); op += ln
+        elif kind == 2:
+            off = int(rng.integers(1, min(op, 65535) + 1)); ln = int(rng.integers(1, 65))
+            out += bytes([((ln - 1) << 2) | 2]) + off.to_bytes(2, "little"); op += ln
+        else:
+            off = int(rng.integers(1, op + 1)) if far else int(rng.integers(1, min(op, 65535) + 1)); ln = int(rng.integers(1, 65))
+            out += bytes([((ln - 1) << 2) | 3]) + off.to_bytes(4, "little"); op += ln
+    return _varint(op) + bytes(out), op
+
+
+def check_random_element_streams(api, o, seeds, target):
+    for seed in seeds:
+        rng = np.random.default_rng(seed)
+        s, n = random_element_stream(rng, target)
+        want = o.decode(s, 1 << 30)
+        assert len(want) == n
+        assert api.decode(s, 1 << 30) == want, seed
+        cut = int(rng.integers(len(s) // 2, len(s)))
+        check_raw_decode_parity(api, o, s[:cut])
+        b = bytearray(s); b[int(rng.integers(5, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        check_raw_decode_parity(api, o, bytes(b))

@@ -106,3 +106,7 @@ def test_raw_multiblock(emu_api, oracle):
     P.check_raw_multiblock(emu_api, oracle, oracle.ref_snappycpp(),
                            [alice[:140000], rng.integers(0, 256, 135000, dtype=np.uint8).tobytes(),
                             alice[:66000] + rng.integers(0, 256, 70000, dtype=np.uint8).tobytes() + alice[:3000]], fuzz=3)
+
+
+def test_raw_random_element_streams(emu_api, oracle):
+    P.check_random_element_streams(emu_api, oracle, range(4), 150000)

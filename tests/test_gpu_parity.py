@@ -274,3 +274,9 @@ def test_device_mixed_sizes_batch(dc, oracle):
     for i in range(len(lens)):
         exp = oracle.encode(src[offs[i]:offs[i] + lens[i]])
         assert h[i * stride:i * stride + out_len[i]].tobytes() == exp, (i, lens[i])
+
+
+def test_raw_random_element_streams(gpu_api, oracle):
+    """Valid raw streams that are not block structured (and their corruptions): discovery must hand them to the single-warp decoder."""
+    P.check_random_element_streams(gpu_api, oracle, range(12), 400000)
+    P.check_random_element_streams(gpu_api, oracle, range(100, 103), 3000000)
