@@ -740,8 +740,9 @@ inline uint32_t mask_crc(uint32_t c) { return ((c >> 15) | (c << 17)) + snb::kCr
 // so that they overlap each other and the copies (H2D in order on s_in, D2H in order on s_out).
 // first_bad receives the index of the first chunk with a non-zero status (or -1).
 constexpr int kDecInFlight = 4;
+// d_resident: the input is already in device memory at this address (same offsets as `in`): no H2D of the payload.
 int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_t* out, int verify,
-                       int64_t* first_bad, int32_t* bad_status) {
+                       int64_t* first_bad, int32_t* bad_status, const uint8_t* d_resident = nullptr) {
   *first_bad = -1;
   const size_t count = chunks.size();
   if (!count) return SNB_OK;
@@ -780,10 +781,10 @@ int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_
     size_t cnt = j - i;
     uint64_t in_len = in_end - in_begin, out_len = out_end - out_begin;
     if (k >= (uint64_t)kDecInFlight) CKS(finish(k - kDecInFlight));  // frees slot s (device buffers, host staging + meta)
-    CK(g.in[s].ensure(in_len + 64));
+    if (!d_resident) CK(g.in[s].ensure(in_len + 64));
     CK(g.out[s].ensure(out_len + 64));
     CK(g.h_meta[s].ensure(cnt * (sizeof(snb_chunk) + 4)));
-    if (!pin_in) CK(g.h_in[s].ensure(in_len));
+    if (!pin_in && !d_resident) CK(g.h_in[s].ensure(in_len));
     if (!pin_out) CK(g.h_out[s].ensure(out_len));
     snb_chunk* hm = g.h_meta[s].as<snb_chunk>();
     for (size_t t = 0; t < cnt; t++) {
@@ -794,7 +795,9 @@ int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_
     snb::Chunk* d_chunks = g.chunks.as<snb::Chunk>() + (size_t)s * kHostSlabChunks;
     int32_t* d_status = g.status.as<int32_t>() + (size_t)s * kHostSlabChunks;
     uint32_t* d_outlen = g.outlen.as<uint32_t>() + (size_t)s * kHostSlabChunks;
-    if (pin_in) {
+    if (d_resident) {
+      // nothing to copy
+    } else if (pin_in) {
       CK(cudaMemcpyAsync(g.in[s].p, in + in_begin, in_len, cudaMemcpyHostToDevice, g.s_in));
     } else {
       memcpy(g.h_in[s].p, in + in_begin, in_len);
@@ -804,8 +807,8 @@ int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_
     CK(cudaEventRecord(g.ev_h2d[s], g.s_in));
     cudaStream_t sc = g.s_dec[s];
     CK(cudaStreamWaitEvent(sc, g.ev_h2d[s], 0));
-    CKS(launch_decompress(g.in[s].as<uint8_t>(), g.out[s].as<uint8_t>(), d_chunks, (uint32_t)cnt, verify, d_status,
-                          d_outlen, sc));
+    CKS(launch_decompress(d_resident ? d_resident + in_begin : g.in[s].as<uint8_t>(), g.out[s].as<uint8_t>(), d_chunks,
+                          (uint32_t)cnt, verify, d_status, d_outlen, sc));
     CK(cudaEventRecord(g.ev_comp[s], sc));
     CK(cudaStreamWaitEvent(g.s_out, g.ev_comp[s], 0));
     if (out_len) {
@@ -910,7 +913,7 @@ int host_decode_raw_blocks(const uint8_t* in, size_t n, int br, uint64_t ulen, u
   int64_t bad = -1;
   int32_t bad_status = 0;
   const auto t_c = std::chrono::steady_clock::now();
-  CKS(host_decode_chunks(in, ch, out, 0, &bad, &bad_status));
+  CKS(host_decode_chunks(in, ch, out, 0, &bad, &bad_status, g.raw_in.as<uint8_t>()));   // the stream is already on the device
   if (getenv("SNB_DEBUG_RAW")) {
     const auto t_d = std::chrono::steady_clock::now();
     auto ms = [](auto x, auto y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
