@@ -360,6 +360,21 @@ def run_ours(args):
                "sample": f"whole {n / (1 << 30):g} GiB corpus, best of 2, chunk ranges over {ref.threads} threads",
                "cpu": cpu_model(), "single_thread_value": round((128 << 20) / dt1 / 1e9, 4),
                "uncompress_value": round(n / dtd / 1e9, 4)}
+        try:  # the reference README's `cppLib` comparator: the bundled C++ snappy (raw format), one thread, 128 MiB
+            from oracle import oracle as _o
+            cpp = _o.ref_snappycpp()
+            if cpp is not None:
+                sample = host_in.numpy()[: 128 << 20]
+                t0 = time.perf_counter()
+                enc_cpp = cpp.encode(sample)
+                t1 = time.perf_counter()
+                dec_cpp = cpp.decode(enc_cpp)
+                t2 = time.perf_counter()
+                if dec_cpp is not None and len(dec_cpp) == sample.size:
+                    cpu["cpplib_single_thread_value"] = round(sample.size / (t1 - t0) / 1e9, 4)
+                    cpu["cpplib_single_thread_uncompress_value"] = round(sample.size / (t2 - t1) / 1e9, 4)
+        except Exception:  # noqa: BLE001 -- an optional extra next to the baseline, never a reason to fail the bench
+            pass
 
     if rank != 0:
         if world > 1:
