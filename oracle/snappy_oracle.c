@@ -57,21 +57,28 @@ static inline uint32_t ld32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); re
 static inline uint64_t ld64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
 /* ------------------------------------------------------------------ CRC */
-/* crc32c.c:204-214 (bytewise table loop), :759-763 (mask). */
-static uint32_t crc_tab[256];
-static int crc_ready;
-static void crc_init(void) {
+/* crc32c.c:747 calculate_crc32c -> :676-731 crc32c_sb8_64_bit (slicing by 8: eight table lookups per 8 input
+ * bytes), :204-214 (bytewise table loop, used here for the tail), :759-763 (mask).  Tables are generated instead of
+ * spelled out; table k maps a byte that is followed by k more bytes of zeros. */
+static uint32_t crc_tab[8][256];
+__attribute__((constructor)) static void crc_init(void) {
   for (uint32_t i = 0; i < 256; i++) {
     uint32_t c = i;
     for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? 0x82F63B78u : 0);
-    crc_tab[i] = c;
+    crc_tab[0][i] = c;
   }
-  crc_ready = 1;
+  for (int k = 1; k < 8; k++)
+    for (uint32_t i = 0; i < 256; i++) crc_tab[k][i] = (crc_tab[k - 1][i] >> 8) ^ crc_tab[0][crc_tab[k - 1][i] & 0xff];
 }
 uint32_t orc_masked_crc32c(const uint8_t *p, size_t n) {
-  if (!crc_ready) crc_init();
   uint32_t c = 0xffffffffu;
-  for (size_t i = 0; i < n; i++) c = crc_tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w = ld64(p + i) ^ c; /* little-endian host, as the reference's fast path assumes */
+    c = crc_tab[7][w & 0xff] ^ crc_tab[6][(w >> 8) & 0xff] ^ crc_tab[5][(w >> 16) & 0xff] ^ crc_tab[4][(w >> 24) & 0xff] ^
+        crc_tab[3][(w >> 32) & 0xff] ^ crc_tab[2][(w >> 40) & 0xff] ^ crc_tab[1][(w >> 48) & 0xff] ^ crc_tab[0][w >> 56];
+  }
+  for (; i < n; i++) c = crc_tab[0][(c ^ p[i]) & 0xff] ^ (c >> 8);
   c = ~c;
   return ((c >> 15) | (c << 17)) + 0xa282ead8u;
 }
