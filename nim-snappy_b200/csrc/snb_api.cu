@@ -559,7 +559,8 @@ int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, ui
     CK(g.out[i].ensure((size_t)slab0_chunks * per_block + 65536));
     CK(g.h_flags[i].ensure((size_t)(pieces_per_slab + 1) * 8));
   }
-  CK(g.h_arr.ensure((size_t)(nslab * pieces_per_slab + 1) * 4));
+  constexpr uint64_t kRampPieces = 8;   // extra (small) pieces at the start of a slab
+  CK(g.h_arr.ensure((size_t)(nslab * (pieces_per_slab + kRampPieces) + 1) * 4));
   CK(g.h_meta[0].ensure(64));
   {
     const uint32_t slab = (uint32_t)slab0_chunks;
@@ -582,9 +583,12 @@ int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, ui
     const int s = (int)(k & 1);
     const uint64_t off = k * slab_bytes, len = std::min<uint64_t>(slab_bytes, n - off);
     if (k >= 2) CK(cudaStreamWaitEvent(g.s_in, g.ev_comp[s], 0));  // in[s] consumed by slab k-2
-    uint64_t pi = k * pieces_per_slab;
-    for (uint64_t po = 0; po < len; po += piece_bytes, pi++) {
-      const uint64_t pl = std::min<uint64_t>(piece_bytes, len - po);
+    uint64_t pi = k * (pieces_per_slab + kRampPieces);
+    // the first pieces are small (2, 2, 4, 8, 16 MiB): the encoder warps get their first chunks 0.5 ms earlier
+    uint64_t next_piece = 2ull << 20;
+    for (uint64_t po = 0, pl = 0; po < len; po += pl, pi++) {
+      pl = std::min<uint64_t>(std::min<uint64_t>(next_piece, piece_bytes), len - po);
+      if (po > 0 && next_piece < piece_bytes) next_piece *= 2;
       CK(cudaMemcpyAsync(g.in[s].as<uint8_t>() + po, in + off + po, pl, cudaMemcpyHostToDevice, g.s_in));
       h_arr[pi] = (uint32_t)((off + po + pl + kChunk - 1) / kChunk);
       CK(cudaMemcpyAsync(g.d_arrived, &h_arr[pi], 4, cudaMemcpyHostToDevice, g.s_in));
