@@ -774,7 +774,9 @@ int host_decode_chunks(const uint8_t* in, std::vector<snb_chunk>& chunks, uint8_
     // slab = chunks [i, j): contiguous input range within budget, at most slab_chunks chunks
     size_t j = i;
     uint64_t in_begin = chunks[i].in_off, in_end = in_begin, out_begin = chunks[i].out_off, out_end = out_begin;
-    while (j < count && j - i < slab_chunks) {
+    // the first slabs are small (256, 256, 512 chunks): the first D2H starts after one short copy + one chunk's decode time
+    const uint32_t this_slab = std::min<uint32_t>(slab_chunks, k < 2 ? 256u : (k == 2 ? 512u : slab_chunks));
+    while (j < count && j - i < this_slab) {
       uint64_t e = chunks[j].in_off + chunks[j].in_len;
       if (j > i && e - in_begin > in_budget) break;
       in_end = e;
