@@ -244,6 +244,7 @@ int do_init(int device) {
   CK(cudaFuncSetAttribute(snb::compress_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(snb::compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(snb::compress_kernel5, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(snb::compress_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #ifndef SNB_EMULATE
   {  // do launches block?  (second launch: the first one pays for loading the module)
     SNB_LAUNCH(snb::launch_probe_kernel, 1, 1, 0, g.s0, 0u);
@@ -283,7 +284,8 @@ void prof_collect(int first_pair, int n_pairs, int slot0) {
 
 // ---------------------------------------------------------------- launch geometry
 struct CompressGeom { uint32_t entries, warps, smem_warps, grid; size_t smem; };
-bool use_v5() { return g.compress_algo == 0 || g.compress_algo == 5; }
+bool use_v5() { return g.compress_algo == 0 || g.compress_algo == 5 || g.compress_algo == 6; }   // the streaming (one launch per slab) path
+bool use_pipe() { return g.compress_algo == 0 || g.compress_algo == 6; }   // ... with the resolver / walker kernel (v6)
 CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
   CompressGeom cg;
   uint32_t e = 256;
@@ -449,9 +451,12 @@ int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
     a.total = d_total; a.error = g.d_arrived + 1; a.crc_tables = g.d_tables;
     a.group_shift = kGroupShift; a.chunk0 = (uint32_t)(chunk0 + first);
     if (p) prof_mark(2, st);
+    if (use_pipe()) {
+      const uint32_t pgrid = std::max(1u, std::min((cnt + snb::pipe::kGroups - 1) / snb::pipe::kGroups, (uint32_t)g.sms));
+      SNB_LAUNCH(snb::compress_pipe_kernel, pgrid, snb::pipe::kThreads, snb::pipe::kSmemBytes, st, a);
+    } else
 #ifndef SNB_EMULATE
-    const size_t tbytes = (size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2;
-    if (g.l2_tables && g.l2_persist_max && g.l2_window_max && tbytes) {
+    if (const size_t tbytes = (size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2; g.l2_tables && g.l2_persist_max && g.l2_window_max && tbytes) {
       // the global-memory hash tables are the only randomly re-read data: pin them in L2, let everything else stream
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(std::min(cg.grid, (uint32_t)g.sms)); cfg.blockDim = dim3(cg.warps * 32);

@@ -1587,7 +1587,7 @@ struct StreamArgs {
 
 #ifdef SNB_EMULATE
 __device__ __forceinline__ unsigned long long snb_now_ns() { return 0; }
-__device__ __forceinline__ void snb_sleep(unsigned) {}
+__device__ __forceinline__ void snb_sleep(unsigned) { emu::yield(); }
 __device__ __forceinline__ uint32_t ld_cg32(const uint32_t* p) { return *p; }
 #else
 __device__ __forceinline__ unsigned long long snb_now_ns() {
@@ -2611,3 +2611,5 @@ __global__ void __launch_bounds__(32) raw_validate_kernel(RawWalkArgs a) {
 }
 
 }  // namespace snb
+
+#include "snb_pipe.cuh"

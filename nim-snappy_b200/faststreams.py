@@ -287,10 +287,12 @@ class FastStreams:
             raise MalformedSnappyData("Invalid header value")
         win.consume(len(framingHeader))
 
-        hint = win.avail() if win.eof else win.src.known_len()
+        # bytes still to come = what the window already holds + what the source can still give
+        left = None if win.eof else win.src.known_len()
+        hint = win.avail() if win.eof else (None if left is None else left + win.avail())
         chunks = SLAB_CHUNKS if hint is None else max(1, min(SLAB_CHUNKS, hint // 8 + 1))   # a data frame is >= 8 bytes
-        stage_cap = SLAB_CHUNKS * (maxCompressedFrameDataLen + 4) if hint is None else \
-            min(SLAB_CHUNKS * (maxCompressedFrameDataLen + 4), hint + 16)
+        one_frame = maxCompressedFrameDataLen + 4
+        stage_cap = SLAB_CHUNKS * one_frame if hint is None else max(one_frame, min(SLAB_CHUNKS * one_frame, hint)) + 16
         stage = self._buf("in0", stage_cap), self._buf("in1", stage_cap)
         out_cap = chunks * maxUncompressedFrameDataLen
         out = self._buf("out", out_cap)
@@ -403,6 +405,8 @@ def _walk_slab(win, stage, max_frames=SLAB_CHUNKS):
                 err = MalformedSnappyData("Frame size too low to contain CRC checksum")
             elif cid == 0x01 and data_len - 4 > maxUncompressedFrameDataLen:   # :123-124
                 err = MalformedSnappyData(f"Invalid frame length: {data_len}")
+            elif staged + run + 4 + data_len > stage.size and (staged or run):
+                break                                                      # the slab is full: this frame opens the next one
             else:
                 run += 4 + data_len
                 frames += 1

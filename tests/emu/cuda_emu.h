@@ -254,6 +254,7 @@ static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; retu
 static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}
+static inline void __threadfence_block() {}
 static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
   unsigned long long o = *p; if (o == cmp) *p = v; return o;
 }

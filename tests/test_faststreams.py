@@ -100,3 +100,18 @@ def test_gpu_faststreams_multi_slab(gpu_api, oracle):
     assert got == oracle.fs_uncompress_framed(bytes(bad))
     assert got[1] == "MalformedSnappyData" and 0 < len(got[0]) < n and d.startswith(got[0])
     fs.close()
+
+
+def test_emu_faststreams_seekable_file_over_one_piece(emu_api, oracle):
+    """A seekable file object holding more than one 32 MiB window piece: the staging buffers must be sized from
+    the bytes still to come INCLUDING what the window has already buffered (round-1 advisor finding: a fresh
+    FastStreams raised ValueError on a valid 33.8 MiB stream read from a BytesIO)."""
+    rng = np.random.default_rng(21)
+    d = rng.integers(0, 256, 33 * (1 << 20) + 777, dtype=np.uint8).tobytes()     # incompressible: stored frames
+    stream = oracle.encode_framed(d)
+    assert len(stream) > (32 << 20)
+    fs = _fs(emu_api)                                                             # fresh: no larger pooled buffers
+    out = io.BytesIO()
+    fs.uncompressFramed(io.BytesIO(stream), out, checkIntegrity=False)
+    assert out.getvalue() == d
+    fs.close()
