@@ -65,7 +65,9 @@ void snb_host_free(void *p);
 int snb_masked_crc32c(const uint8_t *buf, size_t n, uint32_t *crc);
 /* snappy.nim:27-64 compress. */
 int snb_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);
-/* snappy.nim:84-110 uncompress. */
+/* snappy.nim:84-110 uncompress.  Limits of the device path (SNB_UNSUPPORTED, never a reference error code): input
+ * below 4 GiB; a stream longer than one block that is NOT block structured (no encoder of this family emits one)
+ * is decoded by a single warp and may announce at most 256 MiB. */
 int snb_uncompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);
 /* snappy.nim:130-155 compressFramed. */
 int snb_compress_framed(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);

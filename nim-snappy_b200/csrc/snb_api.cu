@@ -949,7 +949,7 @@ void snb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.ready) return;
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.tables, &g.group_done, &g.group_end})
+  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.tables, &g.group_done, &g.group_end, &g.raw_in, &g.raw_walk})
     b->release();
   for (int i = 0; i < 4; i++) { g.in[i].release(); g.out[i].release(); g.h_in[i].release(); g.h_out[i].release(); g.h_meta[i].release(); }
   for (PinBuf* b : {&g.h_flags[0], &g.h_flags[1], &g.h_arr}) b->release();
@@ -1053,6 +1053,10 @@ int snb_uncompress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t
   bool done = false;
   CKS(host_decode_raw_blocks(in, n, br, ulen, out, &done));                  // more than one block: block-parallel when possible
   if (done) { *written = (size_t)ulen; return SNB_OK; }
+  if (ulen > snb::kMaxDeviceMessage || (uint64_t)n - (uint64_t)br > snb::kMaxDeviceMessage) {   // before any staging is allocated
+    g.err = "snb_uncompress: a raw stream that is not block structured is decoded by one warp, limit 256 MiB (see snb.h)";
+    return SNB_UNSUPPORTED;
+  }
   int64_t bad = -1;
   int32_t bad_status = 0;
   CKS(host_decode_chunks(in, ch, out, 0, &bad, &bad_status));
@@ -1235,17 +1239,18 @@ int snb_dev_masked_crc32c_chunks(const uint8_t* d_in, uint64_t n, uint32_t* d_cr
   return launch_crc(d_in, nullptr, nullptr, n, (uint32_t)count, d_crc, 1, (cudaStream_t)stream);
 }
 
-void snb_set_profiling(int enabled) { g.profiling = enabled != 0; }
+void snb_set_profiling(int enabled) { std::lock_guard<std::mutex> lk(g_mu); g.profiling = enabled != 0; }
 int snb_get_profile(float* ms, int n) {
+  std::lock_guard<std::mutex> lk(g_mu);
   int k = std::min(n, 6);
   for (int i = 0; i < k; i++) ms[i] = g.prof[i];
   return k;
 }
 uint64_t snb_kernel_launches(void) { return g.launches; }
 uint64_t snb_raw_block_decodes(void) { return g.raw_block_decodes; }
-void snb_set_compress_warps(int warps) { g.compress_warps = warps % 100; if (warps >= 100) g.compress_gwarps = warps / 100 - 1; }
-void snb_set_compress_algo(int algo) { g.compress_algo = algo; }
-void snb_set_thread_min_chunks(int n) { g.thread_min_chunks = n; }
+void snb_set_compress_warps(int warps) { std::lock_guard<std::mutex> lk(g_mu); g.compress_warps = warps % 100; if (warps >= 100) g.compress_gwarps = warps / 100 - 1; }
+void snb_set_compress_algo(int algo) { std::lock_guard<std::mutex> lk(g_mu); g.compress_algo = algo; }
+void snb_set_thread_min_chunks(int n) { std::lock_guard<std::mutex> lk(g_mu); g.thread_min_chunks = n; }
 
 // Page-locked host memory for callers that stream through the host-buffer entry points: pinned buffers are
 // DMA'd directly by snb_compress* / snb_uncompress* (is_pinned), pageable ones go through the driver's staging.

@@ -2175,6 +2175,7 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
 
   const uint8_t* tags = in + br;
   const uint32_t tn = n - br;
+  if (tn == 0) return kInvalidInput;   // a length but no tags: decodeAllTags writes nothing, snappy.nim:104-108 (the window below needs tn >= 1)
   const uint32_t lim = ulen;  // decisions are identical for any cap >= ulen
   uint32_t ip = 0, op = 0;
   // aligned word view of the tag stream: word 0 holds tags[0] at byte `tmis`

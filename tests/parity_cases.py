@@ -77,6 +77,9 @@ def check_malformed(api, o):
     assert api.encode(b"") == b"\x00"                         # :163-165
     assert api.decode(b"\x00") == b""
     assert api.decode(b"") == b""
+    for enc in (b"\x05", b"\x80\x01", b"\xff\xff\x03"):         # a length and no tags at all (snappy.nim:104-108)
+        assert api.decode(enc) == b""
+        check_raw_decode_parity(api, o, enc)
 
 
 def check_framed_fixture(api, o, fixture, source):
