@@ -285,7 +285,7 @@ void prof_collect(int first_pair, int n_pairs, int slot0) {
 // ---------------------------------------------------------------- launch geometry
 struct CompressGeom { uint32_t entries, warps, smem_warps, grid; size_t smem; };
 bool use_v5() { return g.compress_algo == 0 || g.compress_algo == 5 || g.compress_algo == 6; }   // the streaming (one launch per slab) path
-bool use_pipe() { return g.compress_algo == 0 || g.compress_algo == 6; }   // ... with the resolver / walker kernel (v6)
+bool use_pipe() { return g.compress_algo == 6; }   // ... with the resolver / walker kernel (v6): byte-exact, 2x algorithmic DRAM traffic, but 20 GB/s (walker-latency bound) -- not the default
 CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
   CompressGeom cg;
   uint32_t e = 256;

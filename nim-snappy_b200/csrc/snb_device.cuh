@@ -85,6 +85,9 @@ __device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 #endif
+#ifndef SNB_CRC_AFTER
+#define SNB_CRC_AFTER 0
+#endif
 #ifndef SNB_V5_HINT
 #define SNB_V5_HINT 1   // 0: none, 1: L1 hint, 2: L2 hint for the next window's candidates
 #endif
@@ -1756,12 +1759,25 @@ __global__ void __launch_bounds__(kStreamMaxThreads, 1) compress_stream_kernel(S
       __syncwarp();
     }
     uint32_t crc = 0;
+#if !SNB_CRC_AFTER
     if (frame) {
       const unsigned long long ioff = (unsigned long long)job * kMaxBlock;
       const uint32_t len = (uint32_t)((a.c.total_len - ioff) < kMaxBlock ? (a.c.total_len - ioff) : kMaxBlock);
       crc = crc_mask(crc32c_warp(*crc_t, a.crc_tables, a.c.in_base + ioff, len, lane));
     }
+#endif
     const uint32_t total = compress_job<5>(a.c, job, table, lane, 0, tglobal, crc, false);
+#if SNB_CRC_AFTER
+    // The CRC pass reads the chunk AFTER the encoder has walked it: the bytes are still in L2 from the parse, and a
+    // chunk that has only just been dequeued does not occupy 64 KiB of L2 before its first window is looked at.
+    if (frame) {
+      const unsigned long long ioff = (unsigned long long)job * kMaxBlock;
+      const uint32_t len = (uint32_t)((a.c.total_len - ioff) < kMaxBlock ? (a.c.total_len - ioff) : kMaxBlock);
+      crc = crc_mask(crc32c_warp(*crc_t, a.crc_tables, a.c.in_base + ioff, len, lane));
+      uint8_t* hdr = a.c.out_base + (unsigned long long)job * a.c.out_stride;
+      if (lane < 4) hdr[4 + lane] = (uint8_t)(crc >> (8 * lane));
+    }
+#endif
     __syncwarp();
     if (lane == 0) {
       st_release_gpu(a.c.out_len + job, total);   // the frame's bytes before its length

@@ -52,28 +52,46 @@ struct Group {            // shared memory, one per chunk group
   uint32_t ctl;           // (seq << 16) | next window the walker wants (kStop: job over); kExit: kernel done
   uint32_t ack;           // resolvers that have zeroed their share of the table, summed over jobs
   uint32_t in_lo, in_hi;  // the job's input
-  uint32_t tag[kRing];    // per slot: (seq << 16) | window whose record the slot holds
-  uint32_t pad[16 - 4 - kRing > 0 ? 16 - 4 - kRing : 4];
+  uint32_t pad[12];
 };
 constexpr size_t kTableBytes = (size_t)kMaxTableEntries * 2;
 constexpr size_t kRingBytes = (size_t)kRing * 32 * sizeof(uint2);
 constexpr size_t kSmemBytes = kGroups * (kTableBytes + kRingBytes + sizeof(Group)) + sizeof(CrcSmem);
 static_assert(kSmemBytes <= 227 * 1024, "pipe kernel: shared memory");
 
+// Flags and records cross warps through shared memory WITHOUT fences: a fence (MEMBAR.*.CTA) also waits for the
+// issuing warp's global loads and stores in flight -- the resolver's next-window prefetch, the walker's output bytes --
+// i.e. a DRAM round trip per window.  No ordering between different shared-memory words is assumed instead:
+//   * ctl is a single word that carries no data dependency (a cursor position);
+//   * a record is ONE 8-byte word per lane, written by one STS.64 and read by one LDS.64, and carries its own stamp
+//     (window index + job sequence): a lane either sees the whole record of the window it asked for or retries.
+// The two job-level hand-overs (input pointer, table zeroed) happen once per 64 KiB chunk and do use fences.
 #ifdef SNB_EMULATE
-__device__ __forceinline__ uint32_t ld_acquire_cta(const uint32_t* p) { return *(volatile const uint32_t*)p; }
-__device__ __forceinline__ void st_release_cta(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) { return *(volatile const uint32_t*)p; }
+__device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
+__device__ __forceinline__ uint2 ld_record(const uint2* p) { uint2 r; r.x = ((volatile const uint2*)p)->x; r.y = ((volatile const uint2*)p)->y; return r; }
+__device__ __forceinline__ void st_record(uint2* p, uint2 r) { ((volatile uint2*)p)->x = r.x; ((volatile uint2*)p)->y = r.y; }
 __device__ __forceinline__ void spin_pause() { emu::yield(); }
+__device__ __forceinline__ void spin_sleep(unsigned) { emu::yield(); }
 #else
-__device__ __forceinline__ uint32_t ld_acquire_cta(const uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.cta.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_cta(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.cta.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 ld_record(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_record(uint2* p, uint2 r) {
+  asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(r.x), "r"(r.y) : "memory");
 }
 __device__ __forceinline__ void spin_pause() {}
+__device__ __forceinline__ void spin_sleep(unsigned ns) { __nanosleep(ns); }
 #endif
 
 // Match of the 12 bytes a* at position p against the 12 bytes c* at T: length 0..12 and the first byte of the
@@ -87,12 +105,17 @@ __device__ __forceinline__ uint32_t match12(uint32_t a0, uint32_t a1, uint32_t a
 __device__ __forceinline__ uint32_t copy_tag(uint32_t off, uint32_t ml) {
   return off >= 2048 ? (((ml - 1) << 2) | 2u) : (((off >> 8) << 5) | ((ml - 4) << 2) | 1u);
 }
-// record: x = h | T << 16;  y = ml | tag << 8 | literal byte << 16
-__device__ __forceinline__ uint2 make_record(uint32_t h, uint32_t T, uint32_t ml, uint32_t tag, uint32_t a0) {
+// record: x = h | stamp[12..13] << 14 | T << 16;  y = ml | tag << 4 | literal byte << 12 | stamp[0..11] << 20
+// stamp = (seq % 7 + 1) << 11 | window: never 0 (a zeroed slot is never valid), differs between consecutive jobs.
+__device__ __forceinline__ uint32_t stamp_base(uint32_t seq) { return (seq % 7u + 1u) << 11; }   // once per job
+__device__ __forceinline__ uint2 make_record(uint32_t h, uint32_t T, uint32_t ml, uint32_t tag, uint32_t a0, uint32_t stamp) {
   uint2 r;
-  r.x = h | (T << 16);
-  r.y = ml | ((tag & 0xffu) << 8) | ((a0 & 0xffu) << 16);
+  r.x = h | ((stamp >> 12) << 14) | (T << 16);
+  r.y = ml | ((tag & 0xffu) << 4) | ((a0 & 0xffu) << 12) | (stamp << 20);
   return r;
+}
+__device__ __forceinline__ bool record_is(uint2 r, uint32_t stamp) {
+  return (r.y >> 20) == (stamp & 0xfffu) && ((r.x >> 14) & 3u) == (stamp >> 12);
 }
 
 // ------------------------------------------------------------------------------------------ resolver
@@ -103,11 +126,12 @@ __device__ __forceinline__ void resolver_main(Group* g, uint16_t* table, uint2* 
     seq = (seq + 1) & 0xffffu;
     uint32_t c;
     for (;;) {
-      c = ld_acquire_cta(&g->ctl);
+      c = ld_flag(&g->ctl);
       if (c == kExit || (c >> 16) == seq) break;
-      spin_pause();
+      spin_sleep(200);
     }
     if (c == kExit) return;
+    __threadfence_block();   // the job's input pointer was written before ctl
     InView v;
     {
       const uint8_t* in = (const uint8_t*)(((unsigned long long)g->in_hi << 32) | g->in_lo);
@@ -115,22 +139,25 @@ __device__ __forceinline__ void resolver_main(Group* g, uint16_t* table, uint2* 
       v.w = (const uint32_t*)(in - v.mis);
       v.last = (kLen + v.mis - 1) >> 2;
     }
-    {  // zero this warp's share of the table (encoder.nim:237-238)
+    {  // zero this warp's ring slots (no record of an earlier job survives) and its share of the table (encoder.nim:237-238)
+      uint2 z; z.x = 0; z.y = 0;
+      for (uint32_t sl = r; sl < kRing; sl += kResolvers) st_record(&ring[sl * 32 + lane], z);
       uint32_t* t32 = (uint32_t*)table + r * (kMaxTableEntries / 2 / kResolvers);
       for (uint32_t i = lane; i < kMaxTableEntries / 2 / kResolvers; i += 32) t32[i] = 0;
       __syncwarp();
       if (lane == 0) { __threadfence_block(); atomicAdd(&g->ack, 1u); }
     }
     const uint32_t own_q = (lane + v.mis) >> 2, own_s = ((lane + v.mis) & 3) * 8;
+    const uint32_t sbase = stamp_base(seq);
     uint32_t win = r;
     uint32_t Wn = 0, Wn_win = 0xffffffffu;
     for (;;) {
-      c = ld_acquire_cta(&g->ctl);
+      c = ld_flag(&g->ctl);
       if ((c >> 16) != seq) break;
       const uint32_t want = c & 0xffffu;
       if (want == kStop) break;
       if (win < want) win = want + (r + kResolvers - want % kResolvers) % kResolvers;   // the cursor jumped: skip
-      if (win >= kWinMax || win >= want + kRing) { spin_pause(); continue; }
+      if (win >= kWinMax || win >= want + kRing) { spin_sleep(win >= kWinMax ? 1000 : 100); continue; }   // ring full: do not eat the walkers' issue slots
       const uint32_t b = win << 5, p = b + lane;
       const uint32_t W = (Wn_win == win) ? Wn : __ldg(v.w + (b >> 2) + wlane);
       Wn_win = win + kResolvers;
@@ -145,10 +172,7 @@ __device__ __forceinline__ void resolver_main(Group* g, uint16_t* table, uint2* 
       uint32_t c0, c1, c2;
       in_ld12u(v, T, c0, c1, c2);
       const uint32_t ml = match12(a0, a1, a2, c0, c1, c2);
-      const uint32_t slot = win % kRing;
-      ring[slot * 32 + lane] = make_record(h, T, ml, copy_tag(p - T, ml), a0);
-      __syncwarp();
-      if (lane == 0) st_release_cta(&g->tag[slot], (seq << 16) | win);
+      st_record(&ring[(win % kRing) * 32 + lane], make_record(h, T, ml, copy_tag(p - T, ml), a0, sbase | win));
       win += kResolvers;
     }
   }
@@ -166,7 +190,7 @@ __device__ __forceinline__ uint32_t compress_block_v6(const uint8_t* __restrict_
   v.w = (const uint32_t*)(in - v.mis);
   v.last = (kLen + v.mis - 1) >> 2;
   constexpr uint32_t len = kLen, mask = kMask, ip_limit = kIpLimit;
-  const uint32_t seqhi = seq << 16;
+  const uint32_t seqhi = seq << 16, sbase = stamp_base(seq);
   const uint32_t below = (1u << lane) - 1u;
   const uint32_t notbelow = ~below;
   uint32_t op = 0;
@@ -179,7 +203,8 @@ __device__ __forceinline__ uint32_t compress_block_v6(const uint8_t* __restrict_
   uint32_t want_pub = 0;   // the window ctl currently announces (the job starts with 0)
 
   // the table is zero once every resolver has acknowledged this job
-  while (ld_acquire_cta(&g->ack) != seq * kResolvers) spin_pause();
+  while (ld_flag(&g->ack) != seq * kResolvers) spin_pause();
+  __threadfence_block();
 
 #define SNB_FINISH(from)                                                          \
   do {                                                                            \
@@ -269,7 +294,7 @@ __device__ __forceinline__ uint32_t compress_block_v6(const uint8_t* __restrict_
     const uint32_t win = b >> 5;
     if (win != want_pub) {
       want_pub = win;
-      if (lane == 0) st_release_cta(&g->ctl, seqhi | win);
+      if (lane == 0) st_flag(&g->ctl, seqhi | win);
     }
     const uint32_t p = b + lane;
     if (chain && ip == b && !m1_done) {
@@ -280,13 +305,21 @@ __device__ __forceinline__ uint32_t compress_block_v6(const uint8_t* __restrict_
     m1_done = false;
 
     SNB_STAT(0);
-    const uint32_t slot = win % kRing;
-    while (ld_acquire_cta(&g->tag[slot]) != (seqhi | win)) { SNB_STAT(10); spin_pause(); }
-    const uint2 rec = ring[slot * 32 + lane];
+    uint2 rec;
+    {
+      const uint2* rp = ring + (win % kRing) * 32 + lane;
+      const uint32_t stamp = sbase | win;
+      for (;;) {   // every lane needs its own record of THIS window (a warp-wide store may be seen half done)
+        rec = ld_record(rp);
+        if (__all_sync(kFull, record_is(rec, stamp))) break;
+        SNB_STAT(10);
+        spin_pause();
+      }
+    }
     const uint32_t h = rec.x & kMask;
     const uint32_t T = table[h];
-    uint32_t ml = rec.y & 15u, tag = (rec.y >> 8) & 0xffu;
-    const uint32_t lit = rec.y >> 16;
+    uint32_t ml = rec.y & 15u, tag = (rec.y >> 4) & 0xffu;
+    const uint32_t lit = (rec.y >> 12) & 0xffu;
     const uint32_t off = p - T;
     if (T != (rec.x >> 16)) {   // the entry moved after the resolver looked: re-measure against the entry that counts
       SNB_STAT(11);
@@ -461,10 +494,7 @@ __global__ void __launch_bounds__(pipe::kThreads, 1) compress_pipe_kernel(Stream
   pipe::Group* g = (pipe::Group*)(smem + pipe::kGroups * (pipe::kTableBytes + pipe::kRingBytes)) + grp;
   CrcSmem* crc_t = (CrcSmem*)(smem + pipe::kGroups * (pipe::kTableBytes + pipe::kRingBytes + sizeof(pipe::Group)));
   const bool frame = a.c.mode == kModeFrame;
-  if (role == 0 && lane == 0) {
-    g->ctl = 0; g->ack = 0;
-    for (uint32_t i = 0; i < pipe::kRing; i++) g->tag[i] = 0;   // seq 0 is never used by a job
-  }
+  if (role == 0 && lane == 0) { g->ctl = 0; g->ack = 0; }   // seq 0 is never used by a job
   if (frame) crc_stage_tables(crc_t, a.crc_tables);   // ends with __syncthreads()
   else __syncthreads();
   if (role != 0) { pipe::resolver_main(g, table, ring, role - 1, lane); return; }
@@ -497,7 +527,8 @@ __global__ void __launch_bounds__(pipe::kThreads, 1) compress_pipe_kernel(Stream
       if (lane == 0) {
         const unsigned long long ip64 = (unsigned long long)(uintptr_t)(a.c.in_base + ioff);
         g->in_lo = (uint32_t)ip64; g->in_hi = (uint32_t)(ip64 >> 32);
-        pipe::st_release_cta(&g->ctl, seq << 16);
+        __threadfence_block();
+        pipe::st_flag(&g->ctl, seq << 16);
       }
     }
     uint32_t crc = 0;
@@ -508,7 +539,7 @@ __global__ void __launch_bounds__(pipe::kThreads, 1) compress_pipe_kernel(Stream
     });
     __syncwarp();
     if (lane == 0) {
-      if (piped) pipe::st_release_cta(&g->ctl, (seq << 16) | pipe::kStop);
+      if (piped) pipe::st_flag(&g->ctl, (seq << 16) | pipe::kStop);
       st_release_gpu(a.c.out_len + job, total);
       __threadfence();
     }
@@ -516,7 +547,7 @@ __global__ void __launch_bounds__(pipe::kThreads, 1) compress_pipe_kernel(Stream
     stream_place(a, lane);
     __syncwarp();
   }
-  if (lane == 0) pipe::st_release_cta(&g->ctl, pipe::kExit);
+  if (lane == 0) pipe::st_flag(&g->ctl, pipe::kExit);
 }
 
 }  // namespace snb
