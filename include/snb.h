@@ -14,7 +14,9 @@
  *
  * Buffers: the caller owns every buffer; the library never allocates caller-visible memory.
  * Host entry points accept pageable or pinned host memory (pinned is DMA'd directly).
- * `snb_dev_*` entry points take device pointers and run on the given CUDA stream.
+ * `snb_dev_*` entry points take device pointers and run on the given CUDA stream.  They share the library's work
+ * buffers: a call on one stream is ordered behind the previous snb_dev_* call's use of those buffers (an event wait,
+ * no host synchronisation), so calls may be issued on different streams; they do not overlap each other on the GPU.
  */
 #ifndef SNB_H_
 #define SNB_H_
@@ -33,6 +35,7 @@ extern "C" {
 #define SNB_UNKNOWN_CHUNK 4    /* FrameError.unknownChunk */
 #define SNB_CUDA_ERROR 100     /* CUDA runtime failure, no device, library not initialised */
 #define SNB_UNSUPPORTED 101    /* outside the device path's limits */
+#define SNB_TIMEOUT 102        /* the streaming compress kernel gave up waiting for an input piece (copy failure upstream) */
 
 #define SNB_MAX_BLOCK_LEN 65536u            /* codec.nim:14-19 maxBlockLen / maxUncompressedFrameDataLen */
 #define SNB_MAX_COMPRESSED_FRAME_LEN 76490u /* codec.nim:216-219 */
@@ -77,6 +80,30 @@ int snb_compress_framed(const uint8_t *in, size_t n, uint8_t *out, size_t cap, s
 int snb_uncompress_framed(const uint8_t *in, size_t n, uint8_t *out, size_t cap, int check_header,
                           int check_integrity, size_t *read, size_t *written);
 
+/* ---- host-buffer message batches (many small independent messages, e.g. gossip payloads) ------ */
+/* `compress` (snappy.nim:27-64) of `count` messages held in host memory: message i is
+ * in_base[in_off[i] .. +in_len[i]) (at most 65536 bytes, i.e. one block; SNB_UNSUPPORTED otherwise) and its raw
+ * stream (varint + tags) has out_len[i] bytes.
+ *   out_off == NULL  packed output: the streams are written back to back in message order starting at out_base
+ *                    (stream i begins at the sum of out_len[0..i)); the call returns SNB_BUFFER_TOO_SMALL unless
+ *                    out_cap >= sum of snb_max_compressed_len(in_len[i]) (the reference's per-call bound, :44-45).
+ *                    Only the packed bytes cross the PCIe link.
+ *   out_off != NULL  stream i goes to out_base + out_off[i]; status[i] = SNB_BUFFER_TOO_SMALL when fewer than
+ *                    snb_max_compressed_len(in_len[i]) bytes remain between out_off[i] and out_cap.
+ * status[i]: 0 or 1 + ord(CodecError) (codec.nim:56-58).  Pinned in / out buffers are DMA'd directly. */
+int snb_compress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len, size_t count,
+                       uint8_t *out_base, uint64_t out_cap, const uint64_t *out_off, uint32_t *out_len,
+                       int32_t *status);
+/* `uncompress` (snappy.nim:84-110) of `count` raw streams held in host memory.
+ *   out_off == NULL  packed output in message order by the lengths the streams announce (codec.nim:129-138);
+ *                    SNB_BUFFER_TOO_SMALL (whole call) when their sum exceeds out_cap_total; out_cap is ignored.
+ *   out_off != NULL  message i goes to out_base + out_off[i] with room out_cap[i] (required).
+ * status[i]: 0 / SNB_BUFFER_TOO_SMALL / SNB_INVALID_INPUT exactly as the reference's Result; out_len[i] = bytes
+ * produced (0 on error). */
+int snb_uncompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len, size_t count,
+                         uint8_t *out_base, uint64_t out_cap_total, const uint64_t *out_off, const uint32_t *out_cap,
+                         uint32_t *out_len, int32_t *status);
+
 /* ---- device-resident API (inputs and outputs already in HBM) ------------------------------ */
 /* One decodable unit of a framed stream, produced by snb_frame_index (the host-side header
  * walk of snappy.nim:199-265) or by the caller. */
@@ -106,6 +133,23 @@ typedef struct snb_walk {
  * descriptors; returns SNB_BUFFER_TOO_SMALL if more are needed (n_chunks = required). */
 int snb_frame_index(const uint8_t *stream, size_t n, size_t out_cap, int check_header, int check_integrity,
                     snb_chunk *chunks, size_t max_chunks, size_t *n_chunks, snb_walk *walk);
+
+/* The header walk of snappy.nim:199-265 for a stream that is RESIDENT IN HBM (e.g. one just produced by
+ * snb_dev_compress_framed): the chunk list is found on the device (candidate headers in parallel, successor links,
+ * pointer jumping from the first header), so the stream never visits the host.  d_frame_lens / n_frames
+ * (optional): the table snb_dev_compress_framed returned for this stream -- then the positions come from a prefix sum
+ * and only the headers are validated.  Streams the device path does not model (malformed headers, oversize chunks,
+ * a stream that ends inside a chunk) are walked on the host from a copy, so `walk` always has the reference's verdict.
+ * d_chunks: device array of max_chunks descriptors (SNB_BUFFER_TOO_SMALL with *n_chunks = required otherwise).
+ * Synchronises the stream. */
+int snb_dev_frame_index(const uint8_t *d_stream, uint64_t n, uint64_t out_cap, int check_header, int check_integrity,
+                        const uint32_t *d_frame_lens, size_t n_frames, snb_chunk *d_chunks, size_t max_chunks,
+                        size_t *n_chunks, snb_walk *walk, void *stream);
+/* snappy.nim:169-267 uncompressFramed, stream and output both in HBM: device-side header walk + chunk-parallel decode
+ * + CRC verify; status, *read and *written exactly as snb_uncompress_framed.  Synchronises the stream. */
+int snb_dev_uncompress_framed(const uint8_t *d_stream, uint64_t n, uint8_t *d_out, uint64_t out_cap, int check_header,
+                              int check_integrity, const uint32_t *d_frame_lens, size_t n_frames, uint64_t *read,
+                              uint64_t *written, void *stream);
 
 /* compressFramed over a device buffer.  d_out needs snb_max_compressed_len_framed(n) bytes.
  * with_header: emit the 10-byte stream identifier first (shard 0 of a sharded stream).
@@ -148,6 +192,11 @@ uint64_t snb_kernel_launches(void);
 /* Raw streams of more than one block that snb_uncompress decoded block-parallel (block starts found on the device)
  * rather than on a single warp -- for tests and tuning. */
 uint64_t snb_raw_block_decodes(void);
+/* Device-side header walks (snb_dev_frame_index / snb_dev_uncompress_framed) that had to be finished by the host walk. */
+uint64_t snb_frame_index_fallbacks(void);
+/* Debug (env SNB_DEBUG_SPAN=1): %globaltimer nanoseconds between the first CTA start and the last warp exit of the
+ * last streaming compress kernel -- a clock neither CUDA events nor a profiler own.  0 when not enabled. */
+uint64_t snb_debug_kernel_span_ns(void);
 /* Tuning: warps per CTA of the compress kernel for 64 KiB blocks (hash tables are 32 KiB each). */
 void snb_set_compress_warps(int warps);
 /* Tuning / A-B testing of the block encoder: 0 = auto (default: one thread per block with tables in HBM for
@@ -155,6 +204,9 @@ void snb_set_compress_warps(int warps);
  * 2 = window-resolve warp encoder, 3 = one thread per block. */
 void snb_set_compress_algo(int algo);
 void snb_set_thread_min_chunks(int n);
+/* How long the streaming compress kernel waits for a chunk whose host-to-device copy has not landed (default 2000 ms;
+ * then the call returns SNB_TIMEOUT instead of hanging). */
+void snb_set_arrive_timeout_ms(int ms);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNB_LIB") or os.path.join(HERE, "libsnb200.so")  # SNB_LIB: A/B builds of the same CUDA library (tuning only)
 
 OK, BUFFER_TOO_SMALL, INVALID_INPUT, CRC_MISMATCH, UNKNOWN_CHUNK = 0, 1, 2, 3, 4
-CUDA_ERROR, UNSUPPORTED = 100, 101
+CUDA_ERROR, UNSUPPORTED, TIMEOUT = 100, 101, 102
 
 
 class SnbChunk(C.Structure):
@@ -46,7 +46,11 @@ SIGNATURES = {
     "snb_uncompress": (_i, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "snb_compress_framed": (_i, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "snb_uncompress_framed": (_i, [_vp, _sz, _vp, _sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),
+    "snb_compress_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _u64, _vp, _vp, _vp]),
+    "snb_uncompress_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _u64, _vp, _vp, _vp, _vp]),
     "snb_frame_index": (_i, [_vp, _sz, _sz, _i, _i, C.POINTER(SnbChunk), _sz, C.POINTER(_sz), C.POINTER(SnbWalk)]),
+    "snb_dev_frame_index": (_i, [_vp, _u64, _u64, _i, _i, _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(SnbWalk), _vp]),
+    "snb_dev_uncompress_framed": (_i, [_vp, _u64, _vp, _u64, _i, _i, _vp, _sz, C.POINTER(_u64), C.POINTER(_u64), _vp]),
     "snb_dev_compress_framed": (_i, [_vp, _u64, _vp, _u64, _i, _vp, _vp, C.POINTER(_u64), _vp]),
     "snb_dev_uncompress_chunks": (_i, [_vp, C.POINTER(SnbChunk), _sz, _vp, _i, _vp, _vp]),
     "snb_dev_compress_batch": (_i, [_vp, _vp, _vp, _sz, C.c_uint32, _vp, _vp, _vp, _vp]),
@@ -59,9 +63,12 @@ SIGNATURES = {
     "snb_get_profile": (_i, [C.POINTER(C.c_float), _i]),
     "snb_kernel_launches": (_u64, []),
     "snb_raw_block_decodes": (_u64, []),
+    "snb_frame_index_fallbacks": (_u64, []),
+    "snb_debug_kernel_span_ns": (_u64, []),
     "snb_set_compress_warps": (None, [_i]),
     "snb_set_compress_algo": (None, [_i]),
     "snb_set_thread_min_chunks": (None, [_i]),
+    "snb_set_arrive_timeout_ms": (None, [_i]),
 }
 
 

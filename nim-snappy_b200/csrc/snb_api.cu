@@ -83,14 +83,19 @@ struct Ctx {
   uint32_t* d_counters = nullptr;
   int counter_next = 0;
   uint64_t* d_total = nullptr;  // 4 device scalars
+  unsigned long long* d_span = nullptr;   // 2 device scalars: in-kernel %globaltimer span of the last streaming compress kernel (debug)
+  bool span_on = false;
   DevBuf scratch, lens, offs, crcs, chunks, status, outlen, tables, in[4], out[4];
   PinBuf h_in[4], h_out[4], h_meta[4];
   DevBuf group_done, group_end;     // streaming compress: per-group placement counters / end offsets
   uint64_t raw_block_decodes = 0;
+  uint64_t index_fallbacks = 0;     // device-side header walks that ended in the host walk
   DevBuf raw_in, raw_walk;          // raw multi-block discovery: the stream, and bitmap / per-segment / per-block tables
   PinBuf h_flags[2], h_arr;         // host-mapped group-complete flags per slab parity; arrival values per piece
   uint32_t* d_arrived = nullptr;    // chunks whose input has landed (streaming compress), then a timeout flag
   cudaEvent_t ev_reset = nullptr;
+  cudaEvent_t ev_dev = nullptr;     // end of the last snb_dev_* call's use of the shared work buffers (scratch, lens, tables, counters ...)
+  bool dev_pending = false;
   cudaEvent_t ev_h2d[4] = {}, ev_comp[4] = {}, ev_d2h[4] = {};
   cudaEvent_t ev_prof[12] = {};
   bool profiling = false;
@@ -104,6 +109,7 @@ struct Ctx {
   int l2_tables = 1;                              // keep the encoder's global-memory hash tables resident in L2
   float l2_ratio = 0.f;                           // 0: derive from the carve-out and the table bytes
   uint32_t dec_slab_chunks = 1024;  // host decode pipeline: chunks per H2D | kernel | D2H slab (64 MiB of output: short fill / drain)
+  int arrive_timeout_ms = 2000;     // streaming compress: a chunk whose input has not landed after this long ends the call with SNB_TIMEOUT
   int thread_min_chunks = 1 << 30;  // auto mode: batches at least this large use one thread per block (tables in HBM)
   std::string err;
 };
@@ -238,9 +244,12 @@ int do_init(int device) {
   CK(cudaMemcpy(g.d_hdr, kStreamHeader, 10, cudaMemcpyHostToDevice));
   CK(cudaMalloc((void**)&g.d_counters, kNumCounters * sizeof(uint32_t)));
   CK(cudaMalloc((void**)&g.d_total, 4 * sizeof(uint64_t)));
+  CK(cudaMalloc((void**)&g.d_span, 2 * sizeof(unsigned long long)));
+  g.span_on = getenv("SNB_DEBUG_SPAN") != nullptr;
   CK(cudaMalloc((void**)&g.d_arrived, 4 * sizeof(uint32_t)));
   CK(cudaMemset(g.d_arrived, 0, 4 * sizeof(uint32_t)));
   CK(cudaEventCreateWithFlags(&g.ev_reset, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&g.ev_dev, cudaEventDisableTiming));
   CK(cudaFuncSetAttribute(snb::compress_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(snb::compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(snb::compress_kernel5, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -261,6 +270,23 @@ int do_init(int device) {
   return SNB_OK;
 }
 int need_init() { return g.ready ? SNB_OK : do_init(-1); }
+
+// The snb_dev_* calls run on the CALLER's stream but share one set of work buffers (g_mu only serialises the enqueue).
+// Every such call therefore starts behind the previous one's last use of those buffers, whatever stream that was on,
+// and the host-buffer calls (which use the library's own streams) wait for it on the host.
+int dev_begin(cudaStream_t st) {
+  if (g.dev_pending) CK(cudaStreamWaitEvent(st, g.ev_dev, 0));
+  return SNB_OK;
+}
+int dev_end(cudaStream_t st) {
+  CK(cudaEventRecord(g.ev_dev, st));
+  g.dev_pending = true;
+  return SNB_OK;
+}
+int host_begin() {
+  if (g.dev_pending) { CK(cudaEventSynchronize(g.ev_dev)); g.dev_pending = false; }
+  return SNB_OK;
+}
 
 // A zeroed work-queue counter for one persistent launch.
 int next_counter(cudaStream_t st, uint32_t** out) {
@@ -450,6 +476,13 @@ int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
     a.host_flags = h_flags ? h_flags + first / kGroupChunks : nullptr;
     a.total = d_total; a.error = g.d_arrived + 1; a.crc_tables = g.d_tables;
     a.group_shift = kGroupShift; a.chunk0 = (uint32_t)(chunk0 + first);
+    a.arrive_timeout_ns = (unsigned long long)std::max(1, g.arrive_timeout_ms) * 1000000ull;
+    a.span = nullptr;
+    if (g.span_on) {
+      const unsigned long long init[2] = {~0ull, 0ull};
+      CK(cudaMemcpyAsync(g.d_span, init, sizeof init, cudaMemcpyHostToDevice, st));
+      a.span = g.d_span;
+    }
     if (p) prof_mark(2, st);
     if (use_pipe()) {
       const uint32_t pgrid = std::max(1u, std::min((cnt + snb::pipe::kGroups - 1) / snb::pipe::kGroups, (uint32_t)g.sms));
@@ -652,7 +685,7 @@ int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, ui
   CK(cudaStreamSynchronize(g.s0));
   CK(cudaStreamSynchronize(g.s_out));
   if (dbg_e2e) fprintf(stderr, "host_compress: all streams drained at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
-  if (*g.h_meta[0].as<uint32_t>() != 0) { g.err = "streaming compress: timed out waiting for input pieces"; return SNB_CUDA_ERROR; }
+  if (*g.h_meta[0].as<uint32_t>() != 0) { g.err = "streaming compress: timed out waiting for input pieces (a host-to-device copy did not arrive)"; return SNB_TIMEOUT; }
   return SNB_OK;
 }
 
@@ -936,6 +969,415 @@ int host_decode_raw_blocks(const uint8_t* in, size_t n, int br, uint64_t ulen, u
   return SNB_OK;
 }
 
+// ---------------------------------------------------------------- device-side header walk (snb_frameidx.cuh)
+// Index of a framed stream that lives in HBM.  d_chunks == nullptr: the descriptors go to g.chunks (grown as needed).
+// Fast path on the device; whatever it does not model falls back to a host walk of a copy (exact by construction).
+// Synchronises `st`.  *d_out_chunks receives where the descriptors are.
+struct DevIndex { snb_walk w; size_t n_chunks; snb::Chunk* d_chunks; bool used_fallback; std::vector<uint8_t> host_copy; };
+
+int dev_frame_index(const uint8_t* d_stream, uint64_t n, uint64_t out_cap, int check_header, int check_integrity,
+                    const uint32_t* d_frame_lens, size_t n_frames, snb_chunk* d_user_chunks, size_t max_chunks,
+                    cudaStream_t st, DevIndex& r) {
+  using namespace snb::fidx;
+  memset(&r.w, 0, sizeof r.w);
+  r.n_chunks = 0; r.d_chunks = (snb::Chunk*)d_user_chunks; r.used_fallback = false;
+  const uint64_t start = check_header ? 10 : 0;
+  auto fallback = [&]() -> int {   // exact: the reference's walk over a host copy
+    r.used_fallback = true;
+    g.index_fallbacks++;
+    r.host_copy.resize((size_t)n);
+    if (n) CK(cudaMemcpyAsync(r.host_copy.data(), d_stream, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    WalkOut o;
+    walk_framed(r.host_copy.data(), (size_t)n, (size_t)out_cap, check_header, check_integrity, o);
+    r.w = o.w; r.n_chunks = o.chunks.size();
+    if (!d_user_chunks) { CK(g.chunks.ensure(std::max<size_t>(1, o.chunks.size()) * sizeof(snb_chunk))); r.d_chunks = g.chunks.as<snb::Chunk>(); }
+    else if (o.chunks.size() > max_chunks) return SNB_BUFFER_TOO_SMALL;
+    if (!o.chunks.empty()) {
+      CK(cudaMemcpyAsync(r.d_chunks, o.chunks.data(), o.chunks.size() * sizeof(snb_chunk), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    return SNB_OK;
+  };
+  if (n <= start || n > (1ull << 40)) return fallback();
+  const uint32_t nblocks = (uint32_t)((n - start + kScanBytes - 1) / kScanBytes);
+  const bool hinted = d_frame_lens != nullptr && n_frames > 0 && n_frames < (1u << 30);
+  // work memory (g.raw_walk is free here: raw multi-block discovery never runs concurrently under g_mu)
+  Args a;
+  a.s = d_stream; a.n = n; a.start = start; a.out_cap = out_cap; a.nblocks = nblocks;
+  a.check_integrity = check_integrity ? 1u : 0u;
+  CK(g.h_meta[0].ensure(256));
+  Summary* hs = g.h_meta[0].as<Summary>();
+  size_t n_cand = 0;
+  // Block tables (sizes known up front) live in g.raw_walk, the per-candidate arrays (sized after the scan) in
+  // g.raw_in -- both are free here: raw multi-block discovery never runs concurrently (g_mu).
+  const size_t cand_limit = hinted ? n_frames : (size_t)(n >> 6) + (1u << 20);
+  const size_t blocks_cap = std::max<size_t>(nblocks, (cand_limit + 256) / 256) + 2;
+  {
+    CK(g.raw_walk.ensure(256 + blocks_cap * 12 + (hinted ? 0 : (size_t)nblocks * kBlockCands * 8) + 256));
+    uint8_t* b = g.raw_walk.as<uint8_t>();
+    a.sum = (Summary*)b; b += 256;
+    a.blk_off = (unsigned long long*)b; b += blocks_cap * 8;
+    a.cand_tmp = (unsigned long long*)b; b += hinted ? 0 : (size_t)nblocks * kBlockCands * 8;
+    a.blk_count = (uint32_t*)b;
+  }
+  auto carve = [&](size_t cand_cap) -> int {
+    CK(g.raw_in.ensure(cand_cap * (8 + 8 + 4 * 5) + 256));
+    uint8_t* b = g.raw_in.as<uint8_t>();
+    a.cand = (unsigned long long*)b; b += cand_cap * 8;
+    a.ooff = (unsigned long long*)b; b += cand_cap * 8;
+    a.nxt[0] = (uint32_t*)b; b += cand_cap * 4;
+    a.nxt[1] = (uint32_t*)b; b += cand_cap * 4;
+    a.mark = (uint32_t*)b; b += cand_cap * 4;
+    a.chain = (uint32_t*)b; b += cand_cap * 4;
+    a.ulen = (uint32_t*)b; b += cand_cap * 4;
+    return SNB_OK;
+  };
+  Summary init;
+  memset(&init, 0, sizeof init);
+  init.first_unfit = 0xffffffffu;
+  uint32_t chain_len = 0;
+  unsigned long long* d_tot = (unsigned long long*)g.d_total + 3;
+  if (hinted) {
+    n_cand = n_frames;
+    CKS(carve(n_cand + 1));
+    CK(cudaMemcpyAsync(a.sum, &init, sizeof init, cudaMemcpyHostToDevice, st));
+    // frame i starts at start + sum of the earlier frame sizes; ooff is scratch for those offsets until the describe steps
+    SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, st, d_frame_lens, (uint64_t*)a.ooff, (uint32_t)n_cand, (const uint64_t*)nullptr, (uint64_t)start, (uint64_t*)d_tot);
+    count_launch();
+    SNB_LAUNCH(hint_kernel, (n_cand + 255) / 256, 256, 0, st, a, (const unsigned long long*)a.ooff, d_frame_lens, (uint32_t)n_cand);
+    count_launch();
+    chain_len = (uint32_t)n_cand;
+  } else {
+    CK(cudaMemcpyAsync(a.sum, &init, sizeof init, cudaMemcpyHostToDevice, st));
+    SNB_LAUNCH(scan_kernel, nblocks, kScanThreads, 0, st, a); count_launch();
+    SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, st, a.blk_count, (uint64_t*)a.blk_off, nblocks, (const uint64_t*)nullptr, 0ull, (uint64_t*)d_tot);
+    count_launch();
+    CK(cudaMemcpyAsync(hs, a.sum, sizeof(Summary), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((uint8_t*)hs + 128, d_tot, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    n_cand = (size_t)*(unsigned long long*)((uint8_t*)hs + 128);
+    if (hs->overflow || n_cand == 0 || n_cand > cand_limit) return fallback();
+    CKS(carve(n_cand + 1));
+    SNB_LAUNCH(gather_kernel, nblocks, 256, 0, st, a); count_launch();
+    const uint32_t cg = (uint32_t)((n_cand + 255) / 256);
+    SNB_LAUNCH(link_kernel, cg, 256, 0, st, a, (uint32_t)n_cand); count_launch();
+    uint32_t rounds = 1;
+    while ((1ull << rounds) < n_cand + 1) rounds++;
+    for (uint32_t k = 0; k <= rounds; k++) { SNB_LAUNCH(reach_kernel, cg, 256, 0, st, a, (uint32_t)n_cand, k & 1u); count_launch(); }
+    SNB_LAUNCH(chain_count_kernel, cg, 256, 0, st, a, (uint32_t)n_cand); count_launch();
+    SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, st, a.blk_count, (uint64_t*)a.blk_off, cg, (const uint64_t*)nullptr, 0ull, (uint64_t*)d_tot);
+    count_launch();
+    CK(cudaMemcpyAsync((uint8_t*)hs + 128, d_tot, 8, cudaMemcpyDeviceToHost, st));
+    SNB_LAUNCH(chain_write_kernel, cg, 256, 0, st, a, (uint32_t)n_cand); count_launch();
+    CK(cudaStreamSynchronize(st));
+    chain_len = (uint32_t)*(unsigned long long*)((uint8_t*)hs + 128);
+    if (chain_len == 0) return fallback();
+  }
+  CK(cudaGetLastError());
+  // describe
+  const uint32_t hg = (chain_len + 255) / 256, hg1 = (chain_len + 1 + 255) / 256;
+  SNB_LAUNCH(ulen_kernel, hg, 256, 0, st, a, chain_len); count_launch();
+  SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, st, a.ulen, (uint64_t*)a.ooff, chain_len, (const uint64_t*)nullptr, 0ull, (uint64_t*)d_tot);
+  count_launch();
+  SNB_LAUNCH(fit_kernel, hg, 256, 0, st, a, chain_len); count_launch();
+  SNB_LAUNCH(desc_count_kernel, hg1, 256, 0, st, a, chain_len); count_launch();
+  SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, st, a.blk_count, (uint64_t*)a.blk_off, hg1, (const uint64_t*)nullptr, 0ull, (uint64_t*)d_tot);
+  count_launch();
+  if (!d_user_chunks) {
+    CK(g.chunks.ensure((size_t)(chain_len + 1) * sizeof(snb_chunk)));
+    r.d_chunks = g.chunks.as<snb::Chunk>();
+    a.max_chunks = chain_len + 1;
+  } else a.max_chunks = (uint32_t)std::min<size_t>(max_chunks, 0xffffffffu);
+  a.chunks = r.d_chunks;
+  SNB_LAUNCH(desc_write_kernel, hg1, 256, 0, st, a, chain_len); count_launch();
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hs, a.sum, sizeof(Summary), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync((uint8_t*)hs + 128, d_tot, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const size_t n_data = (size_t)*(unsigned long long*)((uint8_t*)hs + 128);
+  const bool unfit = hs->first_unfit < chain_len;
+  if (getenv("SNB_DEBUG_INDEX"))
+    fprintf(stderr, "frame index: n=%llu cand=%zu chain=%u data=%zu overflow=%u header_ok=%u reached_end=%u first_unfit=%u written=%llu stop=%llu\n",
+            (unsigned long long)n, n_cand, chain_len, n_data, hs->overflow, hs->header_ok, hs->reached_end, hs->first_unfit, hs->written, hs->stop_pos);
+  if (hs->overflow || (check_header && !hs->header_ok) || (!hs->reached_end && !unfit)) return fallback();
+  r.n_chunks = n_data;
+  r.w.written = hs->written;
+  r.w.read = hs->stop_pos;
+  if (unfit) {   // snappy.nim:219-229 (compressed) / :244-254 (stored: the CRC is checked before the room)
+    uint8_t h16[16] = {0};
+    const uint64_t left = n - hs->stop_pos;
+    CK(cudaMemcpyAsync(h16, d_stream + hs->stop_pos, (size_t)std::min<uint64_t>(16, left), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    r.w.partial = 1;
+    if (h16[0] == 0x01 && check_integrity) {
+      snb_chunk c;
+      c.in_off = hs->stop_pos + 8; c.out_off = hs->written; c.in_len = (le32(h16) >> 8) - 4; c.out_cap = c.in_len;
+      c.crc = le32(h16 + 4); c.kind = snb::kKindVerifyOnly;
+      if (d_user_chunks && n_data + 1 > max_chunks) { r.n_chunks = n_data + 1; return SNB_BUFFER_TOO_SMALL; }
+      CK(cudaMemcpyAsync(r.d_chunks + n_data, &c, sizeof c, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      r.n_chunks = n_data + 1;
+      r.w.crc_first = 1;
+    }
+  }
+  if (d_user_chunks && r.n_chunks > max_chunks) return SNB_BUFFER_TOO_SMALL;
+  return SNB_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer message batches (BASELINE config 4)
+// `count` independent raw-format messages in host memory (snappy.nim:27-64 / :84-110 per message).  Slabs of messages
+// go through the GPU double buffered: H2D of the slab's input span (s_in), one kernel sequence (s_dec[slot]), D2H of the
+// slab's PACKED output (s_out) -- the three stages of neighbouring slabs overlap.  Inputs are copied as one span when
+// the messages are dense in it (the usual packed batch), otherwise gathered through pinned staging.
+constexpr size_t kBatchSlabBytes = 128u << 20;     // input bytes per slab
+constexpr size_t kBatchSlabMsgs = 1u << 17;        // messages per slab (bounds the descriptor tables)
+
+struct BatchSlab { size_t first, cnt; uint64_t span_lo, span_hi, in_bytes, out_base; bool gather; };
+
+// Splits [0, count) into slabs; a slab's span is [min offset, max end) of its messages.
+void batch_slabs(const uint64_t* off, const uint32_t* len, size_t count, std::vector<BatchSlab>& slabs) {
+  size_t i = 0;
+  while (i < count) {
+    BatchSlab b{i, 0, off[i], off[i] + len[i], 0, 0, false};
+    while (i < count && b.cnt < kBatchSlabMsgs) {
+      const uint64_t lo = std::min(b.span_lo, off[i]), hi = std::max(b.span_hi, off[i] + len[i]);
+      if (b.cnt && (b.in_bytes + len[i] > kBatchSlabBytes)) break;
+      b.span_lo = lo; b.span_hi = hi; b.in_bytes += len[i]; b.cnt++; i++;
+    }
+    b.gather = (b.span_hi - b.span_lo) > 2 * b.in_bytes + (1u << 20);   // sparse in its span: copy message by message
+    slabs.push_back(b);
+  }
+}
+
+// Stage one slab's input on the device at g.in[slot]; rel[i] = offset of message i inside the device buffer.
+int batch_upload(const uint8_t* in_base, const uint64_t* off, const uint32_t* len, const BatchSlab& b, int slot,
+                 bool pinned, std::vector<uint64_t>& rel) {
+  rel.resize(b.cnt);
+  if (!b.gather) {
+    const uint64_t n = b.span_hi - b.span_lo;
+    CK(g.in[slot].ensure(n + 64));
+    for (size_t t = 0; t < b.cnt; t++) rel[t] = off[b.first + t] - b.span_lo;
+    if (n) {
+      if (pinned) CK(cudaMemcpyAsync(g.in[slot].p, in_base + b.span_lo, n, cudaMemcpyHostToDevice, g.s_in));
+      else {
+        CK(g.h_in[slot].ensure(n));
+        memcpy(g.h_in[slot].p, in_base + b.span_lo, n);
+        CK(cudaMemcpyAsync(g.in[slot].p, g.h_in[slot].p, n, cudaMemcpyHostToDevice, g.s_in));
+      }
+    }
+  } else {
+    CK(g.in[slot].ensure(b.in_bytes + 64));
+    CK(g.h_in[slot].ensure(b.in_bytes + 64));
+    uint64_t pos = 0;
+    for (size_t t = 0; t < b.cnt; t++) {
+      rel[t] = pos;
+      memcpy(g.h_in[slot].as<uint8_t>() + pos, in_base + off[b.first + t], len[b.first + t]);
+      pos += len[b.first + t];
+    }
+    if (pos) CK(cudaMemcpyAsync(g.in[slot].p, g.h_in[slot].p, pos, cudaMemcpyHostToDevice, g.s_in));
+  }
+  return SNB_OK;
+}
+
+int host_compress_batch(const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len, size_t count,
+                        uint8_t* out_base, uint64_t out_cap, const uint64_t* out_off, uint32_t* out_len,
+                        int32_t* status) {
+  // snappy.nim:41-45 per message: a message is at most one block here; its room is maxCompressedLen(len)
+  uint64_t need = 0;
+  uint32_t max_len = 0;
+  for (size_t i = 0; i < count; i++) {
+    status[i] = SNB_OK; out_len[i] = 0;
+    if (in_len[i] > kChunk) { g.err = "snb_compress_batch: a message is longer than one 64 KiB block"; return SNB_UNSUPPORTED; }
+    max_len = std::max(max_len, in_len[i]);
+    const uint64_t room = snb_max_compressed_len(in_len[i]);
+    if (out_off) { if (out_off[i] > out_cap || out_cap - out_off[i] < room) status[i] = SNB_BUFFER_TOO_SMALL; }
+    else need += room;
+  }
+  if (!out_off && need > out_cap) return SNB_BUFFER_TOO_SMALL;
+  std::vector<BatchSlab> slabs;
+  batch_slabs(in_off, in_len, count, slabs);
+  const bool pin_in = is_pinned(in_base), pin_out = is_pinned(out_base);
+  const uint64_t stride = (snb_max_compressed_len(max_len) + 15) / 16 * 16;
+  CompressGeom cg = compress_geom(std::max(1u, max_len), (uint32_t)std::min<size_t>(count, kBatchSlabMsgs));
+  CK(g.tables.ensure((size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2 + 256));
+  std::vector<uint64_t> rel;
+  uint64_t out_pos = 0;                         // packed mode: running output offset
+  auto finish = [&](size_t k) -> int {          // slab k's D2H has been enqueued: wait, then deliver
+    const int s = (int)(k & 1);
+    const BatchSlab& b = slabs[k];
+    CK(cudaEventSynchronize(g.ev_d2h[s]));
+    const uint32_t* lens = (const uint32_t*)(g.h_meta[s].as<uint8_t>() + 8);
+    const uint64_t total = *g.h_meta[s].as<uint64_t>();
+    const uint8_t* packed = pin_out && !out_off ? nullptr : g.h_out[s].as<uint8_t>();
+    uint64_t p = 0;
+    for (size_t t = 0; t < b.cnt; t++) {
+      const size_t i = b.first + t;
+      if (status[i] != SNB_OK) { p += lens[t]; continue; }
+      out_len[i] = lens[t];
+      if (out_off) memcpy(out_base + out_off[i], packed + p, lens[t]);
+      p += lens[t];
+    }
+    if (!out_off && !pin_out && total) memcpy(out_base + b.out_base, packed, total);
+    return SNB_OK;
+  };
+  // A(k): upload, kernels, small D2H of (packed size, lengths).  B(k): once the size is known, the payload D2H.
+  // A(k+1) is enqueued before B(k) waits, so the next slab's H2D overlaps this slab's kernels.
+  auto stage_a = [&](size_t k) -> int {
+    BatchSlab& b = slabs[k];
+    const int s = (int)(k & 1);
+    CKS(batch_upload(in_base, in_off, in_len, b, s, pin_in, rel));
+    const size_t cnt = b.cnt;
+    CK(g.h_meta[s].ensure(8 + cnt * 4 + cnt * 12 + 64));
+    uint8_t* hm = g.h_meta[s].as<uint8_t>() + 8 + cnt * 4;   // after the D2H area (total, lens)
+    memcpy(hm, rel.data(), cnt * 8);
+    memcpy(hm + cnt * 8, in_len + b.first, cnt * 4);
+    const size_t per_slot = kBatchSlabMsgs * 24 + 256;        // [off u64 | len u32 | out_len u32 | offs u64] per message
+    CK(g.chunks.ensure(2 * per_slot));
+    uint8_t* dd = g.chunks.as<uint8_t>() + (size_t)s * per_slot;
+    uint64_t* d_off = (uint64_t*)dd; uint32_t* d_len = (uint32_t*)(dd + kBatchSlabMsgs * 8);
+    uint32_t* d_olen = (uint32_t*)(dd + kBatchSlabMsgs * 12); uint64_t* d_offs = (uint64_t*)(dd + kBatchSlabMsgs * 16);
+    CK(cudaMemcpyAsync(d_off, hm, cnt * 8, cudaMemcpyHostToDevice, g.s_in));
+    CK(cudaMemcpyAsync(d_len, hm + cnt * 8, cnt * 4, cudaMemcpyHostToDevice, g.s_in));
+    CK(cudaEventRecord(g.ev_h2d[s], g.s_in));
+    cudaStream_t sc = g.s_dec[s];
+    CK(cudaStreamWaitEvent(sc, g.ev_h2d[s], 0));
+    if (k >= 1) CK(cudaStreamWaitEvent(sc, g.ev_comp[(k - 1) & 1], 0));   // scratch slots, hash tables and d_total[2] are shared by the slabs
+    CK(g.scratch.ensure(kBatchSlabMsgs * stride + 4096));
+    CK(g.out[s].ensure(b.in_bytes + b.in_bytes / 6 + cnt * 32 + 64));
+    snb::CompressArgs a;
+    a.in_base = g.in[s].as<uint8_t>(); a.out_base = g.scratch.as<uint8_t>(); a.in_off = d_off; a.in_len = d_len; a.out_off = nullptr;
+    a.total_len = 0; a.out_stride = stride; a.crc = nullptr; a.out_len = d_olen; a.count = (uint32_t)cnt;
+    a.mode = snb::kModeRawMessage;
+    CKS(next_counter(sc, &a.counter));
+    CompressGeom cgs = compress_geom(std::max(1u, max_len), (uint32_t)cnt);
+    a.table_entries = cgs.entries; a.smem_warps = cgs.smem_warps; a.gtables = g.tables.as<uint16_t>();
+    a.algo = 4; a.defer_stored = 0;
+    SNB_LAUNCH(snb::compress_kernel5, cgs.grid, cgs.warps * 32, cgs.smem, sc, a); count_launch();
+    CK(cudaGetLastError());
+    SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, sc, d_olen, d_offs, (uint32_t)cnt, (const uint64_t*)nullptr, 0ull, g.d_total + 2);
+    count_launch();
+    const uint32_t cgrid = std::max(1u, std::min((uint32_t)((cnt + 7) / 8), (uint32_t)g.sms * 8));
+    SNB_LAUNCH(snb::compact_warp_kernel, cgrid, 256, 0, sc, g.scratch.as<uint8_t>(), stride, d_olen, d_offs, g.out[s].as<uint8_t>(), (uint32_t)cnt);
+    count_launch();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(g.h_meta[s].p, g.d_total + 2, 8, cudaMemcpyDeviceToHost, sc));
+    CK(cudaMemcpyAsync(g.h_meta[s].as<uint8_t>() + 8, d_olen, cnt * 4, cudaMemcpyDeviceToHost, sc));
+    CK(cudaEventRecord(g.ev_comp[s], sc));
+    return SNB_OK;
+  };
+  auto stage_b = [&](size_t k) -> int {
+    BatchSlab& b = slabs[k];
+    const int s = (int)(k & 1);
+    CK(cudaEventSynchronize(g.ev_comp[s]));
+    const uint64_t total = *g.h_meta[s].as<uint64_t>();
+    b.out_base = out_pos;
+    if (total) {
+      if (pin_out && !out_off) CK(cudaMemcpyAsync(out_base + out_pos, g.out[s].p, total, cudaMemcpyDeviceToHost, g.s_out));
+      else { CK(g.h_out[s].ensure(total)); CK(cudaMemcpyAsync(g.h_out[s].p, g.out[s].p, total, cudaMemcpyDeviceToHost, g.s_out)); }
+    }
+    CK(cudaEventRecord(g.ev_d2h[s], g.s_out));
+    if (!out_off) out_pos += total;
+    return SNB_OK;
+  };
+  for (size_t k = 0; k < slabs.size(); k++) {
+    if (k >= 2) CKS(finish(k - 2));             // frees slot k & 1 (device in / out, pinned staging, meta)
+    CKS(stage_a(k));
+    if (k >= 1) CKS(stage_b(k - 1));
+  }
+  CKS(stage_b(slabs.size() - 1));
+  for (size_t k = slabs.size() > 2 ? slabs.size() - 2 : 0; k < slabs.size(); k++) CKS(finish(k));
+  CK(cudaStreamSynchronize(g.s_in));
+  CK(cudaStreamSynchronize(g.s_out));
+  return SNB_OK;
+}
+
+int host_uncompress_batch(const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len, size_t count,
+                          uint8_t* out_base, uint64_t out_cap_total, const uint64_t* out_off, const uint32_t* out_cap,
+                          uint32_t* out_len, int32_t* status) {
+  // Output placement.  With out_off / out_cap the caller says where each message goes and how much room it has
+  // (snappy.nim:96-97 is then the kernel's check).  Without them the outputs are packed in message order by the
+  // lengths the streams announce (codec.nim:129-138); a malformed varint gives invalidInput and takes no room.
+  std::vector<uint64_t> ooff(count);
+  std::vector<uint32_t> ocap(count);
+  uint64_t pos = 0;
+  for (size_t i = 0; i < count; i++) {
+    status[i] = SNB_OK; out_len[i] = 0;
+    if (out_off) { ooff[i] = out_off[i]; ocap[i] = out_cap ? out_cap[i] : 0; continue; }
+    uint64_t ul = 0;
+    if (get_varint(in_base + in_off[i], in_len[i], 32, &ul) <= 0) { ooff[i] = pos; ocap[i] = 0; continue; }
+    ooff[i] = pos; ocap[i] = (uint32_t)ul; pos += ul;
+  }
+  if (!out_off && pos > out_cap_total) return SNB_BUFFER_TOO_SMALL;
+  std::vector<BatchSlab> slabs;
+  batch_slabs(in_off, in_len, count, slabs);
+  const bool pin_in = is_pinned(in_base), pin_out = is_pinned(out_base);
+  std::vector<uint64_t> rel;
+  CK(g.chunks.ensure(2 * kBatchSlabMsgs * sizeof(snb_chunk)));
+  CK(g.status.ensure(2 * kBatchSlabMsgs * 4));
+  CK(g.outlen.ensure(2 * kBatchSlabMsgs * 4));
+  struct Span { uint64_t lo, hi; };
+  std::vector<Span> ospan(slabs.size());
+  auto finish = [&](size_t k) -> int {
+    const int s = (int)(k & 1);
+    const BatchSlab& b = slabs[k];
+    CK(cudaEventSynchronize(g.ev_d2h[s]));
+    const int32_t* st = (const int32_t*)(g.h_meta[s].as<uint8_t>() + b.cnt * sizeof(snb_chunk));
+    const uint32_t* ol = (const uint32_t*)(st + b.cnt);
+    const bool direct = pin_out && !out_off;
+    for (size_t t = 0; t < b.cnt; t++) {
+      const size_t i = b.first + t;
+      status[i] = st[t]; out_len[i] = st[t] == SNB_OK ? ol[t] : 0;
+      if (!direct && st[t] == SNB_OK && ol[t]) memcpy(out_base + ooff[i], g.h_out[s].as<uint8_t>() + (ooff[i] - ospan[k].lo), ol[t]);
+    }
+    return SNB_OK;
+  };
+  for (size_t k = 0; k < slabs.size(); k++) {
+    const BatchSlab& b = slabs[k];
+    const int s = (int)(k & 1);
+    if (k >= 2) CKS(finish(k - 2));
+    CKS(batch_upload(in_base, in_off, in_len, b, s, pin_in, rel));
+    Span sp{~0ull, 0};
+    for (size_t t = 0; t < b.cnt; t++) {
+      sp.lo = std::min(sp.lo, ooff[b.first + t]); sp.hi = std::max(sp.hi, ooff[b.first + t] + ocap[b.first + t]);
+    }
+    if (sp.hi < sp.lo) sp = Span{0, 0};
+    ospan[k] = sp;
+    const uint64_t olen = sp.hi - sp.lo;
+    if (olen > (1ull << 32) + (8ull << 30)) { g.err = "snb_uncompress_batch: a slab's outputs span more than 12 GiB (scattered out_off)"; return SNB_UNSUPPORTED; }
+    CK(g.out[s].ensure(olen + 64));
+    CK(g.h_meta[s].ensure(b.cnt * (sizeof(snb_chunk) + 8) + 64));
+    snb_chunk* hm = g.h_meta[s].as<snb_chunk>();
+    for (size_t t = 0; t < b.cnt; t++) {
+      const size_t i = b.first + t;
+      hm[t].in_off = rel[t]; hm[t].out_off = ooff[i] - sp.lo; hm[t].in_len = in_len[i]; hm[t].out_cap = ocap[i];
+      hm[t].crc = 0; hm[t].kind = snb::kKindCompressed;
+    }
+    snb::Chunk* d_chunks = g.chunks.as<snb::Chunk>() + (size_t)s * kBatchSlabMsgs;
+    int32_t* d_status = g.status.as<int32_t>() + (size_t)s * kBatchSlabMsgs;
+    uint32_t* d_outlen = g.outlen.as<uint32_t>() + (size_t)s * kBatchSlabMsgs;
+    CK(cudaMemcpyAsync(d_chunks, hm, b.cnt * sizeof(snb_chunk), cudaMemcpyHostToDevice, g.s_in));
+    CK(cudaEventRecord(g.ev_h2d[s], g.s_in));
+    cudaStream_t sc = g.s_dec[s];
+    CK(cudaStreamWaitEvent(sc, g.ev_h2d[s], 0));
+    CKS(launch_decompress(g.in[s].as<uint8_t>(), g.out[s].as<uint8_t>(), d_chunks, (uint32_t)b.cnt, 0, d_status, d_outlen, sc));
+    CK(cudaEventRecord(g.ev_comp[s], sc));
+    CK(cudaStreamWaitEvent(g.s_out, g.ev_comp[s], 0));
+    if (olen) {
+      if (pin_out && !out_off) CK(cudaMemcpyAsync(out_base + sp.lo, g.out[s].p, olen, cudaMemcpyDeviceToHost, g.s_out));
+      else { CK(g.h_out[s].ensure(olen)); CK(cudaMemcpyAsync(g.h_out[s].p, g.out[s].p, olen, cudaMemcpyDeviceToHost, g.s_out)); }
+    }
+    uint8_t* meta_tail = g.h_meta[s].as<uint8_t>() + b.cnt * sizeof(snb_chunk);
+    CK(cudaMemcpyAsync(meta_tail, d_status, b.cnt * 4, cudaMemcpyDeviceToHost, g.s_out));
+    CK(cudaMemcpyAsync(meta_tail + b.cnt * 4, d_outlen, b.cnt * 4, cudaMemcpyDeviceToHost, g.s_out));
+    CK(cudaEventRecord(g.ev_d2h[s], g.s_out));
+  }
+  for (size_t k = slabs.size() > 2 ? slabs.size() - 2 : 0; k < slabs.size(); k++) CKS(finish(k));
+  CK(cudaStreamSynchronize(g.s_in));
+  CK(cudaStreamSynchronize(g.s_out));
+  return SNB_OK;
+}
+
 }  // namespace
 
 // ======================================================================== C ABI
@@ -954,7 +1396,7 @@ void snb_shutdown(void) {
   for (int i = 0; i < 4; i++) { g.in[i].release(); g.out[i].release(); g.h_in[i].release(); g.h_out[i].release(); g.h_meta[i].release(); }
   for (PinBuf* b : {&g.h_flags[0], &g.h_flags[1], &g.h_arr}) b->release();
   cudaFree(g.d_tables); cudaFree(g.d_hdr); cudaFree(g.d_counters); cudaFree(g.d_total); cudaFree(g.d_arrived);
-  cudaEventDestroy(g.ev_reset);
+  cudaEventDestroy(g.ev_reset); cudaEventDestroy(g.ev_dev); g.dev_pending = false;
   for (int i = 0; i < 4; i++) { cudaEventDestroy(g.ev_h2d[i]); cudaEventDestroy(g.ev_comp[i]); cudaEventDestroy(g.ev_d2h[i]); cudaStreamDestroy(g.s_dec[i]); }
   for (int i = 0; i < 12; i++) cudaEventDestroy(g.ev_prof[i]);
   cudaStreamDestroy(g.s0); cudaStreamDestroy(g.s_in); cudaStreamDestroy(g.s_out);
@@ -1007,6 +1449,7 @@ int snb_is_framed_stream(const uint8_t* in, size_t n) { return n >= 10 && memcmp
 int snb_masked_crc32c(const uint8_t* buf, size_t n, uint32_t* crc) {
   std::lock_guard<std::mutex> lk(g_mu);
   CKS(need_init());
+  CKS(host_begin());
   uint32_t c = 0;
   CKS(host_crc(buf, n, &c));
   *crc = mask_crc(c);
@@ -1018,6 +1461,7 @@ int snb_compress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* 
   if ((uint64_t)n > 0xffffffffull) return SNB_INVALID_INPUT;                // snappy.nim:41-42
   if ((uint64_t)cap < snb_max_compressed_len(n)) return SNB_BUFFER_TOO_SMALL;  // :44-45
   CKS(need_init());
+  CKS(host_begin());
   uint64_t pos = (uint64_t)put_varint32(out, (uint32_t)n);                  // :49-50
   CKS(host_compress(in, n, out, &pos, snb::kModeRawBlock));
   *written = (size_t)pos;
@@ -1028,6 +1472,7 @@ int snb_compress_framed(const uint8_t* in, size_t n, uint8_t* out, size_t cap, s
   std::lock_guard<std::mutex> lk(g_mu);
   if ((uint64_t)cap < snb_max_compressed_len_framed((int64_t)n)) return SNB_BUFFER_TOO_SMALL;  // :139-140
   CKS(need_init());
+  CKS(host_begin());
   memcpy(out, kStreamHeader, 10);                                            // :142
   uint64_t pos = 10;
   CKS(host_compress(in, n, out, &pos, snb::kModeFrame));
@@ -1039,6 +1484,7 @@ int snb_uncompress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t
   std::lock_guard<std::mutex> lk(g_mu);
   *written = 0;
   CKS(need_init());
+  CKS(host_begin());
   if ((uint64_t)n > 0xffffffffull) { g.err = "snb_uncompress: input larger than 4 GiB"; return SNB_UNSUPPORTED; }
   std::vector<snb_chunk> ch(1);
   ch[0].in_off = 0; ch[0].out_off = 0; ch[0].in_len = (uint32_t)n;
@@ -1082,7 +1528,7 @@ int snb_uncompress_framed(const uint8_t* in, size_t n, uint8_t* out, size_t cap,
   *read = 0; *written = 0;
   WalkOut o;
   walk_framed(in, n, cap, check_header, check_integrity, o);
-  if (!o.chunks.empty() || o.w.big_crc_len) CKS(need_init());
+  if (!o.chunks.empty() || o.w.big_crc_len) { CKS(need_init()); CKS(host_begin()); }
   int64_t bad = -1;
   int32_t bad_status = 0;
   CKS(host_decode_chunks(in, o.chunks, out, check_integrity, &bad, &bad_status));
@@ -1112,6 +1558,7 @@ int snb_dev_compress_framed(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uin
   if (cap < snb_max_compressed_len_framed((int64_t)n) - (with_header ? 0 : 10)) return SNB_BUFFER_TOO_SMALL;
   CKS(need_init());
   cudaStream_t st = (cudaStream_t)stream;
+  CKS(dev_begin(st));
   prof_begin();
   if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
   uint64_t base = 0;
@@ -1126,6 +1573,7 @@ int snb_dev_compress_framed(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uin
     else CKS(dev_compress_contig(d_in, n, snb::kModeFrame, d_out, base, d_frame_lens, st));
   }
   if (d_written) CK(cudaMemcpyAsync(d_written, g.d_total, 8, cudaMemcpyDeviceToDevice, st));
+  CKS(dev_end(st));
   if (written || g.profiling) {
     CK(g.h_meta[0].ensure(64));
     CK(cudaMemcpyAsync(g.h_meta[0].p, g.d_total, 8, cudaMemcpyDeviceToHost, st));
@@ -1144,6 +1592,7 @@ int snb_dev_uncompress_chunks(const uint8_t* d_in, const snb_chunk* h_chunks, si
   if (!count) return SNB_OK;
   if (count > 0xffffffffull) return SNB_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
+  CKS(dev_begin(st));
   prof_begin();
   if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
   CK(g.chunks.ensure(count * sizeof(snb_chunk)));
@@ -1159,6 +1608,67 @@ int snb_dev_uncompress_chunks(const uint8_t* d_in, const snb_chunk* h_chunks, si
   return SNB_OK;
 }
 
+int snb_dev_frame_index(const uint8_t* d_stream, uint64_t n, uint64_t out_cap, int check_header, int check_integrity,
+                        const uint32_t* d_frame_lens, size_t n_frames, snb_chunk* d_chunks, size_t max_chunks,
+                        size_t* n_chunks, snb_walk* walk, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  CKS(need_init());
+  cudaStream_t st = (cudaStream_t)stream;
+  CKS(dev_begin(st));
+  prof_begin();
+  DevIndex r;
+  int rc = dev_frame_index(d_stream, n, out_cap, check_header, check_integrity, d_frame_lens, n_frames, d_chunks,
+                           max_chunks, st, r);
+  if (n_chunks) *n_chunks = r.n_chunks;
+  if (walk) *walk = r.w;
+  g.prof[5] = (float)g.call_launches;
+  return rc;
+}
+
+// uncompressFramed (snappy.nim:169-267) of a stream that is resident in HBM: device-side header walk, chunk-parallel
+// decode + CRC, then the reference's result rules -- the same ones snb_uncompress_framed applies for host buffers.
+int snb_dev_uncompress_framed(const uint8_t* d_stream, uint64_t n, uint8_t* d_out, uint64_t out_cap, int check_header,
+                              int check_integrity, const uint32_t* d_frame_lens, size_t n_frames, uint64_t* read,
+                              uint64_t* written, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  *read = 0; *written = 0;
+  CKS(need_init());
+  cudaStream_t st = (cudaStream_t)stream;
+  CKS(dev_begin(st));
+  prof_begin();
+  if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
+  DevIndex r;
+  CKS(dev_frame_index(d_stream, n, out_cap, check_header, check_integrity, d_frame_lens, n_frames, nullptr, 0, st, r));
+  const size_t count = r.n_chunks;
+  std::vector<int32_t> status(count);
+  if (count) {
+    if (count > 0xffffffffull) return SNB_UNSUPPORTED;
+    CK(g.status.ensure(count * 4));
+    CK(g.outlen.ensure(count * 4));
+    CKS(launch_decompress(d_stream, d_out, r.d_chunks, (uint32_t)count, check_integrity, g.status.as<int32_t>(),
+                          g.outlen.as<uint32_t>(), st));
+    CK(cudaMemcpyAsync(status.data(), g.status.p, count * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    prof_collect(8, 1, 4);
+  }
+  g.prof[5] = (float)g.call_launches;
+  for (size_t i = 0; i < count; i++) {
+    if (status[i] == 0) continue;
+    // first failing chunk in stream order decides; the intact prefix is reported like snb_uncompress_framed does
+    std::vector<snb_chunk> one(1);
+    CK(cudaMemcpy(one.data(), r.d_chunks + i, sizeof(snb_chunk), cudaMemcpyDeviceToHost));
+    *read = one[0].in_off - 8; *written = one[0].out_off;
+    return status[i] == SNB_CRC_MISMATCH ? SNB_CRC_MISMATCH : SNB_INVALID_INPUT;
+  }
+  if (r.w.big_crc_len) {   // only the host walk (fallback) produces this: oversize stored chunk, CRC outranks the length
+    uint32_t c = 0;
+    CKS(host_crc(r.host_copy.data() + r.w.big_crc_off, (size_t)r.w.big_crc_len, &c));
+    if (mask_crc(c) != r.w.big_crc) return SNB_CRC_MISMATCH;
+  }
+  *read = r.w.read; *written = r.w.written;
+  return r.w.status;
+}
+
 int snb_dev_compress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, size_t count,
                            uint32_t max_len, uint8_t* d_out, const uint64_t* d_out_off, uint32_t* d_out_len,
                            void* stream) {
@@ -1168,6 +1678,7 @@ int snb_dev_compress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const 
   if (count > 0xffffffffull) return SNB_UNSUPPORTED;
   if (max_len == 0 || max_len > kChunk) max_len = (uint32_t)kChunk;
   cudaStream_t st = (cudaStream_t)stream;
+  CKS(dev_begin(st));
   prof_begin();
   if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
   snb::CompressArgs a;
@@ -1187,6 +1698,7 @@ int snb_dev_compress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const 
   count_launch();
   CK(cudaGetLastError());
   prof_mark(3, st);
+  CKS(dev_end(st));
   if (g.profiling) {
     CK(cudaStreamSynchronize(st));
     prof_collect(2, 1, 1);
@@ -1203,6 +1715,7 @@ int snb_dev_uncompress_batch(const uint8_t* d_in, const uint64_t* d_in_off, cons
   if (!count) return SNB_OK;
   if (count > 0xffffffffull) return SNB_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
+  CKS(dev_begin(st));
   prof_begin();
   if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
   CK(g.chunks.ensure(count * sizeof(snb_chunk)));
@@ -1211,12 +1724,33 @@ int snb_dev_uncompress_batch(const uint8_t* d_in, const uint64_t* d_in_off, cons
   count_launch();
   CK(cudaGetLastError());
   CKS(launch_decompress(d_in, d_out, g.chunks.as<snb::Chunk>(), (uint32_t)count, 0, d_status, d_out_len, st));
+  CKS(dev_end(st));
   if (g.profiling) {
     CK(cudaStreamSynchronize(st));
     prof_collect(8, 1, 4);
     g.prof[5] = (float)g.call_launches;
   }
   return SNB_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer message batches
+int snb_compress_batch(const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len, size_t count,
+                       uint8_t* out_base, uint64_t out_cap, const uint64_t* out_off, uint32_t* out_len,
+                       int32_t* status) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!count) return SNB_OK;
+  CKS(need_init());
+  CKS(host_begin());
+  return host_compress_batch(in_base, in_off, in_len, count, out_base, out_cap, out_off, out_len, status);
+}
+int snb_uncompress_batch(const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len, size_t count,
+                         uint8_t* out_base, uint64_t out_cap_total, const uint64_t* out_off, const uint32_t* out_cap,
+                         uint32_t* out_len, int32_t* status) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!count) return SNB_OK;
+  CKS(need_init());
+  CKS(host_begin());
+  return host_uncompress_batch(in_base, in_off, in_len, count, out_base, out_cap_total, out_off, out_cap, out_len, status);
 }
 
 int snb_dev_uncompressed_lens(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, size_t count,
@@ -1248,8 +1782,20 @@ int snb_get_profile(float* ms, int n) {
 }
 uint64_t snb_kernel_launches(void) { return g.launches; }
 uint64_t snb_raw_block_decodes(void) { return g.raw_block_decodes; }
+uint64_t snb_frame_index_fallbacks(void) { return g.index_fallbacks; }
+// Debug (SNB_DEBUG_SPAN=1): nanoseconds between the first CTA's start and the last warp's exit of the last streaming
+// compress kernel, read from %globaltimer inside the kernel; synchronises the device.  0 when not enabled.
+uint64_t snb_debug_kernel_span_ns(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g.ready || !g.span_on) return 0;
+  unsigned long long v[2] = {0, 0};
+  if (cudaDeviceSynchronize() != cudaSuccess) return 0;
+  if (cudaMemcpy(v, g.d_span, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return v[1] > v[0] ? v[1] - v[0] : 0;
+}
 void snb_set_compress_warps(int warps) { std::lock_guard<std::mutex> lk(g_mu); g.compress_warps = warps % 100; if (warps >= 100) g.compress_gwarps = warps / 100 - 1; }
 void snb_set_compress_algo(int algo) { std::lock_guard<std::mutex> lk(g_mu); g.compress_algo = algo; }
+void snb_set_arrive_timeout_ms(int ms) { std::lock_guard<std::mutex> lk(g_mu); g.arrive_timeout_ms = ms; }
 void snb_set_thread_min_chunks(int n) { std::lock_guard<std::mutex> lk(g_mu); g.thread_min_chunks = n; }
 
 // Page-locked host memory for callers that stream through the host-buffer entry points: pinned buffers are

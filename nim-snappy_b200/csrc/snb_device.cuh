@@ -1586,6 +1586,8 @@ struct StreamArgs {
   const CrcTables* crc_tables;
   uint32_t group_shift;
   uint32_t chunk0;                       // index of this slab's first chunk in `arrived` units
+  unsigned long long arrive_timeout_ns;  // how long a warp waits for its chunk's input before it gives up (error flag, SNB_TIMEOUT)
+  unsigned long long* span;              // optional: [0] = min %globaltimer at CTA start, [1] = max at CTA end (a clock the profiler does not own)
 };
 
 #ifdef SNB_EMULATE
@@ -1728,7 +1730,6 @@ __device__ __forceinline__ void stream_place(const StreamArgs& a, uint32_t lane)
 #define SNB_STREAM_MAXT 704
 #endif
 constexpr uint32_t kStreamMaxThreads = SNB_STREAM_MAXT;
-constexpr unsigned long long kArriveTimeoutNs = 20ull * 1000 * 1000 * 1000;
 __global__ void __launch_bounds__(kStreamMaxThreads, 1) compress_stream_kernel(StreamArgs a) {
   SNB_DYN_SMEM(smem);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1738,12 +1739,13 @@ __global__ void __launch_bounds__(kStreamMaxThreads, 1) compress_stream_kernel(S
                         : a.c.gtables + ((size_t)blockIdx.x * (blockDim.x / 32 - a.c.smem_warps) + (warp - a.c.smem_warps)) * a.c.table_entries;
   CrcSmem* crc_t = (CrcSmem*)(smem + (size_t)a.c.smem_warps * a.c.table_entries * 2);
   const bool frame = a.c.mode == kModeFrame;
+  if (a.span && threadIdx.x == 0) atomicMin(a.span, snb_now_ns());
   if (frame) crc_stage_tables(crc_t, a.crc_tables);
   for (;;) {
     uint32_t job = 0;
     if (lane == 0) job = atomicAdd(a.c.counter, 1u);
     job = __shfl_sync(kFull, job, 0);
-    if (job >= a.c.count) return;
+    if (job >= a.c.count) { if (a.span && lane == 0) atomicMax(a.span + 1, snb_now_ns()); return; }
     if (a.arrived) {  // the chunk's bytes may still be on their way
       if (lane == 0) {
         const volatile uint32_t* arr = (const volatile uint32_t*)a.arrived;
@@ -1751,7 +1753,7 @@ __global__ void __launch_bounds__(kStreamMaxThreads, 1) compress_stream_kernel(S
           const unsigned long long t0 = snb_now_ns();
           while (*arr <= a.chunk0 + job) {
             snb_sleep(500);
-            if (snb_now_ns() - t0 > kArriveTimeoutNs) { *(volatile uint32_t*)a.error = 1; break; }
+            if (snb_now_ns() - t0 > a.arrive_timeout_ns) { *(volatile uint32_t*)a.error = 1; break; }
           }
         }
         __threadfence();
@@ -2398,6 +2400,15 @@ __global__ void __launch_bounds__(SNB_DEC_THREADS, SNB_DEC_MINB) decompress_kern
   }
 }
 
+// Message batches: gather slot i (at i*stride, lens[i] bytes) to dst + offs[i], one WARP per message (messages are a
+// few KiB: a CTA per message, as compact_kernel does for 64 KiB frames, would idle 7 of its 8 warps).
+__global__ void __launch_bounds__(256) compact_warp_kernel(const uint8_t* scratch, uint64_t stride, const uint32_t* lens,
+                                                           const uint64_t* offs, uint8_t* dst, uint32_t count) {
+  const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (uint32_t job = blockIdx.x * wpb + (threadIdx.x >> 5); job < count; job += gridDim.x * wpb)
+    warp_copy(dst + offs[job], scratch + (uint64_t)job * stride, lens[job], lane);
+}
+
 // Build Chunk descriptors for a raw batch from offset/length tables (device-side helper).
 __global__ void make_chunks_kernel(const uint64_t* in_off, const uint32_t* in_len, const uint64_t* out_off,
                                    const uint32_t* out_cap, Chunk* chunks, uint32_t count) {
@@ -2630,3 +2641,4 @@ __global__ void __launch_bounds__(32) raw_validate_kernel(RawWalkArgs a) {
 }  // namespace snb
 
 #include "snb_pipe.cuh"
+#include "snb_frameidx.cuh"

@@ -1,0 +1,299 @@
+// snb_frameidx.cuh -- the framed header walk (snappy.nim:199-265, codec.nim:166-172) for a stream that is resident
+// in HBM (included by snb_device.cuh).
+//
+// The reference walks the chunk headers as a linked list: header -> 24-bit length -> next header.  Done serially on
+// the device that is one dependent DRAM load per 64 KiB chunk (~16 ms for the 1 GiB corpus, longer than decoding it);
+// done on the host it costs a D2H of the whole stream.  Here the list is found in parallel:
+//
+//   scan      every stream position is tested for "could be a chunk header": a type the walk accepts (0x00, 0x01,
+//             >= 0x80) whose length fits the stream and, for data chunks, passes the reference's own size / varint
+//             checks (skippable chunks: up to 64 KiB).  Random payload bytes pass about once in 500 positions;
+//             candidates are kept in stream order.
+//   link      a candidate's successor is the candidate at position + 4 + length (binary search), the end of the
+//             stream, or nothing.
+//   reach     starting from the first header the reachable set doubles per round (pointer jumping): after
+//             ceil(log2(candidates)) rounds exactly the headers the serial walk would visit are marked, in order.
+//   describe  one thread per reached header fills its chunk descriptor; a prefix sum of the announced lengths gives
+//             the output offsets and the first chunk that does not fit the caller's room (snappy.nim:219-229, :253-254).
+//
+// Anything the fast path does not model -- a header the walk would reject, a stream that ends inside a chunk, too
+// many candidates -- is reported, and the host then runs walk_framed on a copy: statuses and the (read, written)
+// contract are always the reference's.
+#pragma once
+
+namespace snb {
+namespace fidx {
+
+constexpr uint32_t kScanThreads = 256;
+constexpr uint32_t kScanBytes = 32768;          // stream bytes per CTA
+constexpr uint32_t kBlockCands = 256;           // candidate slots per CTA (random payload: ~80 per 32 KiB)
+constexpr uint32_t kEnd = 0xfffffffeu, kDead = 0xffffffffu;
+constexpr uint32_t kMaxSkippable = 1u << 16;    // longest skippable chunk the candidate scan considers
+
+struct Summary {            // device -> host, one small D2H
+  uint32_t overflow;        // a CTA found more candidates than it has slots for
+  uint32_t header_ok;       // the 10-byte stream identifier is present (when asked for)
+  uint32_t n_cand;
+  uint32_t chain_len;       // reached headers (data chunks and skippable ones)
+  uint32_t reached_end;     // the chain ends exactly at the end of the stream
+  uint32_t n_chunks;        // descriptors written (data chunks that fit)
+  uint32_t first_unfit;     // index (in chain order) of the first data chunk that does not fit out_cap, or 0xffffffff
+  uint32_t pad;
+  unsigned long long written;   // output bytes of the listed chunks
+  unsigned long long stop_pos;  // stream position where the listing stopped (header of the unfit chunk, or n)
+};
+
+struct Args {
+  const uint8_t* s;
+  unsigned long long n, start, out_cap;
+  uint32_t nblocks;
+  uint32_t* blk_count;             // [nblocks]
+  unsigned long long* blk_off;     // [nblocks] exclusive scan of blk_count
+  unsigned long long* cand_tmp;    // [nblocks * kBlockCands]
+  unsigned long long* cand;        // [n_cand] sorted positions
+  uint32_t* nxt[2];                // successor index (kEnd / kDead / candidate index), double buffered
+  uint32_t* mark;                  // reached flag per candidate (+ 2 virtual nodes)
+  uint32_t* chain;                 // candidate indices in chain order
+  uint32_t* ulen;                  // announced length per chain node (0 for skippable)
+  unsigned long long* ooff;        // exclusive scan of ulen
+  Chunk* chunks;                   // output descriptors
+  uint32_t max_chunks;
+  uint32_t check_integrity;
+  Summary* sum;
+};
+
+__device__ __forceinline__ uint32_t ld_u8(const uint8_t* p) { return __ldg(p); }
+
+// Is there a chunk header at p that the serial walk would accept and step over?  Same checks as walk_framed /
+// snappy.nim:199-263.  kind: 0 compressed, 1 stored, 2 skippable.
+__device__ __forceinline__ bool header_ok(const uint8_t* s, unsigned long long n, unsigned long long p, uint32_t hdr,
+                                          uint32_t* kind, uint32_t* ulen) {
+  const uint32_t id = hdr & 0xffu, dlen = hdr >> 8;
+  if (n - p < 4 || n - p - 4 < dlen) return false;                // :200-207
+  if (id >= 0x80u) { *kind = 2; *ulen = 0; return true; }          // :262-263
+  if (id > 1u || dlen < 4) return false;                           // :259-260, :210-211, :238-239
+  if (id == 1u) {
+    if (dlen - 4 > kMaxBlock) return false;                        // :244-251 (oversize stored chunk: the host decides)
+    *kind = 1; *ulen = dlen - 4;
+    return true;
+  }
+  // u32 varint at p + 8 (snappy.nim:92-94 via :216), at most min(5, dlen - 4) bytes
+  uint32_t v = 0;
+  const uint32_t avail = dlen - 4;
+  for (uint32_t i = 0; i < 5; i++) {
+    if (i >= avail) return false;
+    const uint32_t b = ld_u8(s + p + 8 + i);
+    if (i == 4 && (b & 0xf0u)) return false;
+    v |= (b & 0x7fu) << (7 * i);
+    if (!(b & 0x80u)) {
+      if (v > kMaxBlock) return false;                             // :219-222
+      *kind = 0; *ulen = v;
+      return true;
+    }
+  }
+  return false;
+}
+
+// scan: candidates of each 32 KiB piece of the stream, in stream order, into the CTA's slots.
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(Args a) {
+  __shared__ unsigned long long list[kBlockCands];
+  __shared__ uint32_t cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const unsigned long long lo = a.start + (unsigned long long)blockIdx.x * kScanBytes;
+  const unsigned long long hi = lo + kScanBytes < a.n ? lo + kScanBytes : a.n;
+  const uint8_t* s = a.s;
+  const uint32_t mis = (uint32_t)((uintptr_t)(s + lo) & 3);
+  const uint32_t* w = (const uint32_t*)(s + lo - mis);             // aligned view; position lo is byte `mis` of word 0
+  const unsigned long long last_word = (a.n - (lo - mis) - 1) >> 2;  // last word holding a stream byte
+  for (unsigned long long base = 0; lo + base < hi + mis; base += kScanThreads * 4) {
+    const unsigned long long k = (base >> 2) + threadIdx.x;         // this thread's word: view bytes [4k, 4k+4)
+    if (k > last_word) continue;
+    const uint32_t w0 = __ldg(w + k), w1 = k + 1 <= last_word ? __ldg(w + k + 1) : 0u;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+      const unsigned long long vb = 4 * k + j;                      // view byte index
+      if (vb < mis) continue;
+      const unsigned long long p = lo + (vb - mis);
+      if (p >= hi) continue;
+      const uint32_t hdr = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
+      const uint32_t id = hdr & 0xffu;
+      if (id > 1u && id < 0x80u) continue;
+      // A skippable chunk may announce any 24-bit length, so half of all random payload bytes would qualify in a large
+      // stream.  Only short ones (identifier repeats, padding) are candidates; a stream with a longer skippable chunk
+      // simply does not reach its end on the device and is walked by the host.
+      if (id >= 0x80u && (hdr >> 8) > kMaxSkippable) continue;
+      uint32_t kind, ul;
+      if (!header_ok(s, a.n, p, hdr, &kind, &ul)) continue;
+      const uint32_t slot = atomicAdd(&cnt, 1u);
+      if (slot < kBlockCands) list[slot] = p;
+    }
+  }
+  __syncthreads();
+  const uint32_t c = cnt;
+  if (c > kBlockCands) { if (threadIdx.x == 0) { a.sum->overflow = 1; a.blk_count[blockIdx.x] = 0; } return; }
+  // rank sort (c is small): every entry counts the entries before it
+  for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+    const unsigned long long v = list[i];
+    uint32_t r = 0;
+    for (uint32_t j = 0; j < c; j++) r += list[j] < v ? 1u : 0u;
+    a.cand_tmp[(unsigned long long)blockIdx.x * kBlockCands + r] = v;
+  }
+  if (threadIdx.x == 0) {
+    a.blk_count[blockIdx.x] = c;
+    if (blockIdx.x == 0 && a.start == 10) {                         // the stream identifier (snappy.nim:187-194)
+      const uint8_t magic[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};
+      uint32_t ok = a.n >= 10 ? 1u : 0u;
+      for (uint32_t i = 0; ok && i < 10; i++) ok = ld_u8(s + i) == magic[i] ? 1u : 0u;
+      a.sum->header_ok = ok;
+    }
+  }
+}
+
+// gather: CTA slots -> one sorted array.
+__global__ void __launch_bounds__(256) gather_kernel(Args a) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t c = a.blk_count[b];
+  const unsigned long long o = a.blk_off[b];
+  for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) a.cand[o + i] = a.cand_tmp[(unsigned long long)b * kBlockCands + i];
+}
+
+__device__ __forceinline__ uint32_t load_hdr(const uint8_t* s, unsigned long long p) {
+  return ld_u8(s + p) | (ld_u8(s + p + 1) << 8) | (ld_u8(s + p + 2) << 16) | (ld_u8(s + p + 3) << 24);
+}
+
+// link: successor of every candidate; mark the start node.
+__global__ void __launch_bounds__(256) link_kernel(Args a, uint32_t n_cand) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand) return;
+  const unsigned long long p = a.cand[i];
+  const unsigned long long t = p + 4 + (load_hdr(a.s, p) >> 8);
+  uint32_t nx = kDead;
+  if (t == a.n) nx = kEnd;
+  else {
+    uint32_t lo = i + 1, hi = n_cand;                               // first candidate at position >= t
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (a.cand[m] < t) lo = m + 1; else hi = m; }
+    if (lo < n_cand && a.cand[lo] == t) nx = lo;
+  }
+  a.nxt[0][i] = nx;
+  a.mark[i] = (p == a.start) ? 1u : 0u;
+}
+
+// reach, one doubling round: marked nodes mark their current jump target; every jump doubles.
+__global__ void __launch_bounds__(256) reach_kernel(Args a, uint32_t n_cand, uint32_t parity) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand) return;
+  const uint32_t* cur = a.nxt[parity];
+  uint32_t* nxt = a.nxt[parity ^ 1];
+  const uint32_t j = cur[i];
+  if (j < n_cand) {
+    if (a.mark[i]) a.mark[j] = 1u;
+    nxt[i] = cur[j];
+  } else {
+    nxt[i] = j;
+    if (j == kEnd && a.mark[i]) a.sum->reached_end = 1u;   // (only the last chain node ever keeps kEnd as its 1-step target
+  }                                                         //  through all rounds; earlier ones reach it by jumping)
+}
+
+// chain: reached candidates in order (they are sorted by position, and the walk only moves forward).
+__global__ void __launch_bounds__(256) chain_count_kernel(Args a, uint32_t n_cand) {
+  __shared__ uint32_t c;
+  if (threadIdx.x == 0) c = 0;
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cand && a.mark[i]) atomicAdd(&c, 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) a.blk_count[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(256) chain_write_kernel(Args a, uint32_t n_cand) {
+  __shared__ uint32_t flags[256];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  flags[threadIdx.x] = (i < n_cand && a.mark[i]) ? 1u : 0u;
+  __syncthreads();
+  if (!flags[threadIdx.x]) return;
+  uint32_t r = 0;
+  for (uint32_t j = 0; j < threadIdx.x; j++) r += flags[j];
+  a.chain[a.blk_off[blockIdx.x] + r] = i;
+}
+
+// describe, step 1: announced length of every chain node.
+__global__ void __launch_bounds__(256) ulen_kernel(Args a, uint32_t chain_len) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= chain_len) return;
+  const unsigned long long p = a.cand[a.chain[i]];
+  uint32_t kind = 2, ul = 0;
+  header_ok(a.s, a.n, p, load_hdr(a.s, p), &kind, &ul);
+  a.ulen[i] = ul;
+}
+// step 2: first data chunk that does not fit the caller's room (snappy.nim:219-229, :253-254).
+__global__ void __launch_bounds__(256) fit_kernel(Args a, uint32_t chain_len) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= chain_len) return;
+  if (a.ulen[i] && a.ooff[i] + a.ulen[i] > a.out_cap) atomicMin(&a.sum->first_unfit, i);
+}
+// step 3: descriptors of the data chunks before the first unfit one, densely packed (skippable nodes leave no entry).
+// blk_count / blk_off are reused for the per-CTA counts of data chunks.
+__global__ void __launch_bounds__(256) desc_count_kernel(Args a, uint32_t chain_len) {
+  __shared__ uint32_t c;
+  if (threadIdx.x == 0) c = 0;
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lim = a.sum->first_unfit < chain_len ? a.sum->first_unfit : chain_len;
+  if (i < lim) {
+    const unsigned long long p = a.cand[a.chain[i]];
+    if ((ld_u8(a.s + p) & 0xfeu) == 0) atomicAdd(&c, 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) a.blk_count[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(256) desc_write_kernel(Args a, uint32_t chain_len) {
+  __shared__ uint32_t flags[256];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lim = a.sum->first_unfit < chain_len ? a.sum->first_unfit : chain_len;
+  unsigned long long p = 0;
+  uint32_t id = 0xff;
+  if (i < lim) { p = a.cand[a.chain[i]]; id = ld_u8(a.s + p); }
+  flags[threadIdx.x] = id <= 1u ? 1u : 0u;
+  __syncthreads();
+  if (i == lim) {   // where the listing stops: the unfit chunk's header, or the end of the chain
+    a.sum->stop_pos = i < chain_len ? a.cand[a.chain[i]] : a.n;
+    a.sum->written = i < chain_len ? a.ooff[i] : (chain_len ? a.ooff[chain_len - 1] + a.ulen[chain_len - 1] : 0ull);
+  }
+  if (id > 1u) return;
+  uint32_t r = 0;
+  for (uint32_t j = 0; j < threadIdx.x; j++) r += flags[j];
+  const unsigned long long slot = a.blk_off[blockIdx.x] + r;
+  if (slot >= a.max_chunks) return;
+  const uint32_t dlen = load_hdr(a.s, p) >> 8;
+  Chunk c;
+  c.in_off = p + 8; c.out_off = a.ooff[i]; c.in_len = dlen - 4; c.out_cap = a.ulen[i];
+  c.crc = load_hdr(a.s, p + 4); c.kind = id == 0 ? kKindCompressed : kKindStored;
+  a.chunks[slot] = c;
+}
+
+// Chain positions straight from a table of frame sizes (what snb_dev_compress_framed leaves behind): candidate i is
+// the i-th frame, already in chain order.  The describe steps validate every header they touch, so a table that does
+// not belong to the stream is detected (header_ok fails -> ulen 0 and the sizes do not add up) and the caller falls
+// back to the scan.
+__global__ void __launch_bounds__(256) hint_kernel(Args a, const unsigned long long* frame_off, const uint32_t* frame_len,
+                                                   uint32_t n_frames) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_frames) return;
+  const unsigned long long p = frame_off[i];
+  a.cand[i] = p;
+  a.chain[i] = i;
+  uint32_t kind = 2, ul = 0;
+  const bool ok = p + 4 <= a.n && header_ok(a.s, a.n, p, load_hdr(a.s, p), &kind, &ul) &&
+                  (load_hdr(a.s, p) >> 8) + 4 == frame_len[i];
+  if (!ok) a.sum->overflow = 1;     // the table does not describe this stream
+  if (i + 1 == n_frames && ok && p + frame_len[i] == a.n) a.sum->reached_end = 1;
+  if (i == 0 && a.start == 10) {
+    const uint8_t magic[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};
+    uint32_t okh = a.n >= 10 ? 1u : 0u;
+    for (uint32_t k = 0; okh && k < 10; k++) okh = ld_u8(a.s + k) == magic[k] ? 1u : 0u;
+    a.sum->header_ok = okh;
+  }
+}
+
+}  // namespace fidx
+}  // namespace snb

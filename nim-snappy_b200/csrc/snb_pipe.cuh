@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(pipe::kThreads, 1) compress_pipe_kernel(Stream
           const unsigned long long t0 = snb_now_ns();
           while (*arr <= a.chunk0 + job) {
             snb_sleep(500);
-            if (snb_now_ns() - t0 > kArriveTimeoutNs) { *(volatile uint32_t*)a.error = 1; break; }
+            if (snb_now_ns() - t0 > a.arrive_timeout_ns) { *(volatile uint32_t*)a.error = 1; break; }
           }
         }
         __threadfence();

@@ -64,6 +64,34 @@ class DeviceCodec:
                 continue
             return chunks[: n_chunks.value], walk
 
+    def dev_frame_index(self, d_stream, out_cap=None, check_header=True, check_integrity=True, frame_lens=None):
+        """Header walk of a stream resident in HBM (snb_dev_frame_index) -> (device chunk tensor [n, 32] uint8, SnbWalk)."""
+        import torch
+        n = d_stream.numel()
+        if out_cap is None:
+            out_cap = (1 << 62)
+        guess = max(16, n // 8192)
+        while True:
+            d_chunks = torch.empty((guess, C.sizeof(_lib.SnbChunk)), dtype=torch.uint8, device=d_stream.device)
+            n_chunks = C.c_size_t(0)
+            walk = _lib.SnbWalk()
+            st = self.lib.snb_dev_frame_index(_ptr(d_stream), n, out_cap, int(check_header), int(check_integrity),
+                                              _ptr(frame_lens), 0 if frame_lens is None else frame_lens.numel(),
+                                              _ptr(d_chunks), guess, C.byref(n_chunks), C.byref(walk), _stream())
+            if self.lib.check(st) == _lib.BUFFER_TOO_SMALL:
+                guess = n_chunks.value
+                continue
+            return d_chunks[: n_chunks.value], walk
+
+    def uncompress_framed(self, d_stream, d_out, check_header=True, check_integrity=True, frame_lens=None):
+        """uncompressFramed (snappy.nim:169-267), stream and output in HBM -> (status, read, written)."""
+        rd, wr = C.c_uint64(0), C.c_uint64(0)
+        st = self.lib.snb_dev_uncompress_framed(_ptr(d_stream), d_stream.numel(), _ptr(d_out), d_out.numel(),
+                                                int(check_header), int(check_integrity), _ptr(frame_lens),
+                                                0 if frame_lens is None else frame_lens.numel(),
+                                                C.byref(rd), C.byref(wr), _stream())
+        return self.lib.check(st), rd.value, wr.value
+
     def uncompress_chunks(self, d_stream, chunks, d_out, check_integrity=True):
         """Decode walked chunks of a device-resident stream into d_out -> int32 status per chunk."""
         chunks = np.ascontiguousarray(chunks)

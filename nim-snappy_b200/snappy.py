@@ -131,6 +131,82 @@ class Snappy:
         return b"" if isinstance(r, FrameError) else out.tobytes()
 
 
+    # ---- batches of small messages (BASELINE config 4): `compress` / `uncompress` of every message in ONE library call
+    def compressBatch(self, packed, offsets, lengths, output=None):
+        """snappy.nim:27-64 for each message packed[offsets[i] : offsets[i] + lengths[i]].  Packed output mode:
+        -> (output array, out_len uint32[count], status int32[count]); stream i starts at out_len[:i].sum().
+        Raises nothing for reference errors: they are in `status` (1 + ord(CodecError))."""
+        a, pa = _ro(packed)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+        count = ln.size
+        if output is None:
+            output = np.empty(int((32 + ln.astype(np.uint64) + ln // 6).sum()), dtype=np.uint8)
+        o, po = _rw(output)
+        out_len = np.zeros(count, dtype=np.uint32)
+        status = np.zeros(count, dtype=np.int32)
+        st = self.lib.check(self.lib.snb_compress_batch(pa, off.ctypes.data, ln.ctypes.data, count, po, o.size, None,
+                                                         out_len.ctypes.data, status.ctypes.data))
+        if st != 0:
+            return CodecError(st)
+        return o, out_len, status
+
+    def uncompressBatch(self, packed, offsets, lengths, output=None):
+        """snappy.nim:84-110 for each raw stream packed[offsets[i] : +lengths[i]], outputs packed in message order
+        by their announced lengths -> (output array, out_len uint32[count], status int32[count])."""
+        a, pa = _ro(packed)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+        count = ln.size
+        if output is None:
+            total = 0
+            for i in range(count):
+                n = self.uncompressedLen(a[int(off[i]):int(off[i]) + int(ln[i])])
+                total += n if n is not None and n <= 0xFFFFFFFF else 0
+            output = np.empty(max(total, 1), dtype=np.uint8)[:total]
+        o, po = _rw(output)
+        out_len = np.zeros(count, dtype=np.uint32)
+        status = np.zeros(count, dtype=np.int32)
+        st = self.lib.check(self.lib.snb_uncompress_batch(pa, off.ctypes.data, ln.ctypes.data, count, po, o.size, None,
+                                                           None, out_len.ctypes.data, status.ctypes.data))
+        if st != 0:
+            return CodecError(st)
+        return o, out_len, status
+
+    def encodeBatch(self, messages):
+        """`encode` (snappy.nim:66-82) of a list of bytes-like messages -> list of bytes."""
+        lens = np.array([len(m) for m in messages], dtype=np.uint32)
+        offs = np.zeros(len(messages), dtype=np.uint64)
+        if len(messages) > 1:
+            np.cumsum(lens[:-1], out=offs[1:], dtype=np.uint64)
+        packed = np.frombuffer(b"".join(bytes(m) for m in messages), dtype=np.uint8)
+        r = self.compressBatch(packed, offs, lens)
+        if isinstance(r, CodecError):
+            return [b""] * len(messages)
+        out, out_len, status = r
+        ends = np.cumsum(out_len, dtype=np.uint64)
+        return [out[int(e) - int(n):int(e)].tobytes() if st == 0 else b"" for e, n, st in zip(ends, out_len, status)]
+
+    def decodeBatch(self, streams):
+        """`decode` (snappy.nim:112-128) of a list of raw streams -> list of bytes (b"" on error)."""
+        lens = np.array([len(m) for m in streams], dtype=np.uint32)
+        offs = np.zeros(len(streams), dtype=np.uint64)
+        if len(streams) > 1:
+            np.cumsum(lens[:-1], out=offs[1:], dtype=np.uint64)
+        packed = np.frombuffer(b"".join(bytes(m) for m in streams), dtype=np.uint8)
+        r = self.uncompressBatch(packed, offs, lens)
+        if isinstance(r, CodecError):
+            return [b""] * len(streams)
+        out, out_len, status = r
+        res, pos = [], 0
+        for i in range(len(streams)):
+            n = self.uncompressedLen(streams[i])
+            room = n if n is not None and n <= 0xFFFFFFFF else 0
+            res.append(out[pos:pos + int(out_len[i])].tobytes() if status[i] == 0 else b"")
+            pos += room
+        return res
+
+
 _api = Snappy()
 maskedCrc = _api.maskedCrc
 uncompressedLen = _api.uncompressedLen
@@ -144,3 +220,7 @@ compressFramed = _api.compressFramed
 encodeFramed = _api.encodeFramed
 uncompressFramed = _api.uncompressFramed
 decodeFramed = _api.decodeFramed
+compressBatch = _api.compressBatch
+uncompressBatch = _api.uncompressBatch
+encodeBatch = _api.encodeBatch
+decodeBatch = _api.decodeBatch

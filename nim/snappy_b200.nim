@@ -27,8 +27,25 @@ proc snb_uncompress_framed(inp: ptr byte, n: csize_t, outp: ptr byte, cap: csize
 template p(a: openArray[byte]): ptr byte =
   if a.len == 0: nil else: unsafeAddr a[0]
 
+proc snb_last_error(): cstring {.cdecl, importc, dynlib: snbLib.}
+
+type SnbUnavailable* = object of Defect
+  ## Status >= 100: no CUDA device / CUDA runtime failure / outside the device path's limits.  This is NOT a property
+  ## of the input, so it must never surface as `invalidInput` ("malformed data"): the library has no CPU path, and a
+  ## host that may lack a GPU asks `snbAvailable()` once at start-up and keeps the original procs otherwise.
+
+proc snbAvailable*(device = 0): bool =
+  ## True when libsnb200 can run on `device` (binds this process to it: one process per GPU).
+  snb_init(cint device) == 0
+
+proc snbLastError*(): string = $snb_last_error()
+
+template checkEnv(st: cint) =
+  if st >= 100:
+    raise (ref SnbUnavailable)(msg: "libsnb200 status " & $st & ": " & $snb_last_error())
+
 func toCodecError(st: cint): CodecError =
-  # status = 1 + ord(enum); >= 100 (no CUDA device) has no reference equivalent -> invalidInput
+  # status = 1 + ord(enum) (codec.nim:56-58); environment failures were raised by checkEnv before this point
   if st == 1: CodecError.bufferTooSmall else: CodecError.invalidInput
 
 func toFrameError(st: cint): FrameError =
@@ -41,16 +58,19 @@ func toFrameError(st: cint): FrameError =
 proc compress*(input: openArray[byte], output: var openArray[byte]): Result[int, CodecError] =
   var written: csize_t
   let st = snb_compress(p(input), input.len.csize_t, p(output), output.len.csize_t, addr written)
+  checkEnv st
   if st == 0: ok(int written) else: err(toCodecError(st))
 
 proc uncompress*(input: openArray[byte], output: var openArray[byte]): Result[int, CodecError] =
   var written: csize_t
   let st = snb_uncompress(p(input), input.len.csize_t, p(output), output.len.csize_t, addr written)
+  checkEnv st
   if st == 0: ok(int written) else: err(toCodecError(st))
 
 proc compressFramed*(input: openArray[byte], output: var openArray[byte]): Result[int, FrameError] =
   var written: csize_t
   let st = snb_compress_framed(p(input), input.len.csize_t, p(output), output.len.csize_t, addr written)
+  checkEnv st
   if st == 0: ok(int written) else: err(toFrameError(st))
 
 proc uncompressFramed*(input: openArray[byte], output: var openArray[byte],
@@ -59,6 +79,7 @@ proc uncompressFramed*(input: openArray[byte], output: var openArray[byte],
   var read, written: csize_t
   let st = snb_uncompress_framed(p(input), input.len.csize_t, p(output), output.len.csize_t,
                                  cint(checkHeader), cint(checkIntegrity), addr read, addr written)
+  checkEnv st
   if st == 0: ok((int read, int written)) else: err(toFrameError(st))
 
 proc encode*(input: openArray[byte]): seq[byte] =

@@ -342,3 +342,158 @@ def check_random_element_streams(api, o, seeds, target):
         check_raw_decode_parity(api, o, s[:cut])
         b = bytearray(s); b[int(rng.integers(5, len(b)))] ^= 1 << int(rng.integers(0, 8))
         check_raw_decode_parity(api, o, bytes(b))
+
+
+# ---------------------------------------------------------------- host-buffer message batches (snb_compress_batch / snb_uncompress_batch)
+def check_batch(api, o, messages, extra_streams=()):
+    """Every message of a batch: stream == oracle `encode` byte for byte; batch decode of the oracle's streams plus
+    `extra_streams` (malformed ones) == oracle `uncompress` status and bytes per message."""
+    import ctypes as C
+    enc = api.encodeBatch(messages)
+    exp = [o.encode(m) for m in messages]
+    assert enc == exp
+    streams = exp + list(extra_streams)
+    dec = api.decodeBatch(streams)
+    for s, d in zip(streams, dec):
+        n = o.uncompressed_len(s)
+        st_o, out_o = o.uncompress(s, n if n is not None and n < (1 << 24) else 0) if n is not None and n <= 0xFFFFFFFF else (2, b"")
+        assert d == (out_o if st_o == 0 else b""), (s[:12], st_o)
+    # explicit placement + per-message room: bufferTooSmall for exactly the short ones (snappy.nim:96-97)
+    lib = api.lib
+    lens = np.array([len(s) for s in exp], dtype=np.uint32)
+    offs = np.zeros(len(exp), dtype=np.uint64)
+    if len(exp) > 1:
+        np.cumsum(lens[:-1], out=offs[1:], dtype=np.uint64)
+    packed = np.frombuffer(b"".join(exp) or b"\0", dtype=np.uint8)
+    ulen = np.array([len(m) for m in messages], dtype=np.uint32)
+    cap = ulen.copy()
+    short = np.arange(len(exp)) % 3 == 0
+    cap[short & (ulen > 0)] -= 1
+    stride = int(ulen.max()) + 8 if len(exp) else 8
+    ooff = (np.arange(len(exp), dtype=np.uint64) * stride).astype(np.uint64)
+    out = np.zeros(max(1, len(exp) * stride), dtype=np.uint8)
+    out_len = np.zeros(len(exp), dtype=np.uint32)
+    status = np.full(len(exp), -1, dtype=np.int32)
+    st = lib.check(lib.snb_uncompress_batch(packed.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(exp), out.ctypes.data,
+                                            out.size, ooff.ctypes.data, cap.ctypes.data, out_len.ctypes.data, status.ctypes.data))
+    assert st == 0
+    for i, m in enumerate(messages):
+        if short[i] and len(m) > 0:
+            assert status[i] == 1, i
+        else:
+            assert status[i] == 0 and out_len[i] == len(m) and out[i * stride:i * stride + len(m)].tobytes() == bytes(m), i
+    # compress with explicit offsets (slots of the worst-case size)
+    mlens = np.array([len(m) for m in messages], dtype=np.uint32)
+    moffs = np.zeros(len(messages), dtype=np.uint64)
+    if len(messages) > 1:
+        np.cumsum(mlens[:-1], out=moffs[1:], dtype=np.uint64)
+    mpacked = np.frombuffer(b"".join(bytes(m) for m in messages) or b"\0", dtype=np.uint8)
+    cstride = 32 + int(mlens.max()) + int(mlens.max()) // 6 if len(messages) else 32
+    coff = (np.arange(len(messages), dtype=np.uint64) * cstride).astype(np.uint64)
+    cout = np.zeros(max(1, len(messages) * cstride), dtype=np.uint8)
+    clen = np.zeros(len(messages), dtype=np.uint32)
+    cst = np.full(len(messages), -1, dtype=np.int32)
+    st = lib.check(lib.snb_compress_batch(mpacked.ctypes.data, moffs.ctypes.data, mlens.ctypes.data, len(messages), cout.ctypes.data,
+                                          cout.size, coff.ctypes.data, clen.ctypes.data, cst.ctypes.data))
+    assert st == 0 and not cst.any()
+    for i in range(len(messages)):
+        assert cout[i * cstride:i * cstride + clen[i]].tobytes() == exp[i], i
+    # too little total room in packed mode: the whole call says bufferTooSmall (snappy.nim:44-45)
+    if len(messages):
+        tiny = np.zeros(8, dtype=np.uint8)
+        assert lib.snb_compress_batch(mpacked.ctypes.data, moffs.ctypes.data, mlens.ctypes.data, len(messages), tiny.ctypes.data,
+                                      tiny.size, None, clen.ctypes.data, cst.ctypes.data) == 1
+
+
+# ---------------------------------------------------------------- device-side header walk (snb_dev_uncompress_framed)
+def emu_dev_call(lib):
+    """snb_dev_uncompress_framed over host arrays (the emulator's `device` pointers are host pointers)."""
+    import ctypes as C
+
+    def call(stream, cap, check_header=True, check_integrity=True, frame_lens=None):
+        a = np.frombuffer(bytes(stream) + b"\0" * 16, dtype=np.uint8)
+        out = np.zeros(cap + 16, dtype=np.uint8)
+        rd, wr = C.c_uint64(0), C.c_uint64(0)
+        fl = None if frame_lens is None else np.ascontiguousarray(frame_lens, dtype=np.uint32)
+        st = lib.snb_dev_uncompress_framed(a.ctypes.data, len(stream), out.ctypes.data, cap, int(check_header),
+                                           int(check_integrity), None if fl is None else fl.ctypes.data,
+                                           0 if fl is None else fl.size, C.byref(rd), C.byref(wr), None)
+        return lib.check(st), rd.value, wr.value, out[:wr.value].tobytes()
+    return call
+
+
+def gpu_dev_call(dc):
+    import torch
+
+    def call(stream, cap, check_header=True, check_integrity=True, frame_lens=None):
+        d_s = torch.frombuffer(bytearray(bytes(stream) + b"\0" * 16), dtype=torch.uint8).cuda()[: len(stream)]
+        d_out = torch.zeros(cap + 16, dtype=torch.uint8, device="cuda")[:cap]
+        fl = None if frame_lens is None else torch.from_numpy(np.ascontiguousarray(frame_lens, dtype=np.int32)).cuda()
+        st, rd, wr = dc.uncompress_framed(d_s, d_out, check_header, check_integrity, fl)
+        return st, rd, wr, d_out[:wr].cpu().numpy().tobytes()
+    return call
+
+
+def check_dev_framed_decode_parity(call, o, stream, cap, check_header=True, check_integrity=True, frame_lens=None):
+    """Same status / (read, written) / bytes as the oracle's uncompressFramed for a device-resident stream.  On a
+    per-chunk failure the library additionally reports the intact prefix (see snb.h); the oracle has no counts then."""
+    st_o, rd_o, wr_o, out_o = o.uncompress_framed(stream, cap, check_header, check_integrity)
+    st, rd, wr, out = call(stream, cap, check_header, check_integrity, frame_lens)
+    assert st == st_o, (bytes(stream[:24]), cap, st, st_o)
+    if st_o == 0:
+        assert (rd, wr) == (rd_o, wr_o), (rd, wr, rd_o, wr_o)
+        assert out == out_o
+
+
+def check_dev_framed(call, o, datas, rng, fuzz=30, lib=None):
+    for d in datas:
+        s = o.encode_framed(d)
+        n = len(d)
+        fl = []
+        pos = 10
+        while pos < len(s):
+            ln = 4 + (s[pos + 1] | (s[pos + 2] << 8) | (s[pos + 3] << 16))
+            fl.append(ln)
+            pos += ln
+        for cap in sorted({n, n + 5, max(n - 1, 0), 65536, 65535, 0, n // 2}):
+            check_dev_framed_decode_parity(call, o, s, cap)
+            check_dev_framed_decode_parity(call, o, s, cap, check_integrity=False)
+        # a well-formed stream with enough room does not need the host walk -- unless its payload looks like headers all
+        # over (a run of zeros compresses to `fe 01 00` copy elements: every third byte is a plausible skippable chunk),
+        # which overflows the candidate slots and is handed to the host walk by design
+        if lib is not None and len(s) > 10 and len(set(d)) > 1:
+            f0 = lib.snb_frame_index_fallbacks()
+            check_dev_framed_decode_parity(call, o, s, n)
+            check_dev_framed_decode_parity(call, o, s, max(n - 1, 0))
+            check_dev_framed_decode_parity(call, o, s[:10] + b"\xfe\x03\x00\x00abc" + s[10:], n)
+            if fl:
+                check_dev_framed_decode_parity(call, o, s, n, frame_lens=fl)
+            assert lib.snb_frame_index_fallbacks() == f0, "device header walk fell back to the host on a valid stream"
+        if fl:
+            check_dev_framed_decode_parity(call, o, s, n, frame_lens=fl)                   # the compressor's own table
+            check_dev_framed_decode_parity(call, o, s, n, frame_lens=fl[:-1] + [fl[-1] + 1])  # a table that does not fit: ignored
+            check_dev_framed_decode_parity(call, o, s[10:], n, check_header=False, frame_lens=fl)
+        check_dev_framed_decode_parity(call, o, s[10:], n, check_header=False)
+        # skippable / padding / repeated identifier chunks in the middle, unknown chunk types, trailing garbage
+        mid = 10 + (fl[0] if fl else 0)
+        for ins in (b"\xfe\x03\x00\x00abc", HDR, b"\x80\x00\x00\x00", b"\x02\x01\x00\x00x", b"\x7f\x00\x00\x00"):
+            check_dev_framed_decode_parity(call, o, s[:mid] + ins + s[mid:], n)
+        for tail in (b"\x00", b"\xff\x06\x00", b"\x00\x10\x00\x00zz", b"\x01\x02\x00\x00ab"):
+            check_dev_framed_decode_parity(call, o, s + tail, n)
+        for m in mutate_streams(o, s, rng, fuzz):
+            check_dev_framed_decode_parity(call, o, m, n)
+            check_dev_framed_decode_parity(call, o, m, n, check_integrity=False)
+    check_dev_framed_decode_parity(call, o, long_skippable_stream(o, bytes(datas[2]) if len(datas) > 2 else b"x" * 100), 1 << 20)
+    for payload, n in V.INVALID_FRAMED:
+        check_dev_framed_decode_parity(call, o, payload, n, check_header=False)
+        check_dev_framed_decode_parity(call, o, HDR + payload, n)
+    check_dev_framed_decode_parity(call, o, b"", 0)
+    check_dev_framed_decode_parity(call, o, HDR, 0)
+    check_dev_framed_decode_parity(call, o, HDR[:7], 0)
+
+
+def long_skippable_stream(o, data):
+    """A valid stream with a skippable chunk longer than the device scan considers: must still decode (host walk)."""
+    s = o.encode_framed(data)
+    pad = b"\xfe" + (70000).to_bytes(3, "little") + bytes(70000)
+    return s[:10] + pad + s[10:]

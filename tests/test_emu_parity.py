@@ -110,3 +110,22 @@ def test_raw_multiblock(emu_api, oracle):
 
 def test_raw_random_element_streams(emu_api, oracle):
     P.check_random_element_streams(emu_api, oracle, range(4), 150000)
+
+
+def test_host_message_batch(emu_api, oracle):
+    """snb_compress_batch / snb_uncompress_batch (host buffers, packed output): BASELINE config 4 in miniature."""
+    rng = np.random.default_rng(17)
+    src = read_data("geo.protodata") + read_data("alice29.txt")
+    msgs = [b"", b"a", bytes(17)] + [src[o:o + n] for o, n in zip(rng.integers(0, len(src) - 4096, 40), rng.integers(1, 4097, 40))]
+    msgs.append(rng.integers(0, 256, 3000, dtype=np.uint8).tobytes())
+    P.check_batch(emu_api, oracle, msgs, extra_streams=V.MALFORMED_RAW[:8] + [b"\x05", b""])
+
+
+def test_device_side_header_walk(emu_api, oracle):
+    """snb_dev_uncompress_framed: the header walk of snappy.nim:199-265 done on the device (candidate scan, links,
+    pointer jumping) must give the reference's statuses, (read, written) and bytes -- valid streams, every partial-output
+    room, skippable / unknown chunks, trailing bytes, mutated streams; with and without the compressor's frame table."""
+    rng = np.random.default_rng(23)
+    alice = read_data("alice29.txt")
+    datas = [b"", b"abc", alice[:5000], alice[:70000] + rng.integers(0, 256, 66000, dtype=np.uint8).tobytes(), bytes(140000)]
+    P.check_dev_framed(P.emu_dev_call(emu_api.lib), oracle, datas, rng, fuzz=12, lib=emu_api.lib)

@@ -280,3 +280,166 @@ def test_raw_random_element_streams(gpu_api, oracle):
     """Valid raw streams that are not block structured (and their corruptions): discovery must hand them to the single-warp decoder."""
     P.check_random_element_streams(gpu_api, oracle, range(12), 400000)
     P.check_random_element_streams(gpu_api, oracle, range(100, 103), 3000000)
+
+
+# ------------------------------------------------------------------ BASELINE configs 4 and 5 at their sizes
+def test_config4_one_million_messages_host_batch(gpu_api, oracle):
+    """BASELINE configs[3]: 1 M independent 1-4 KiB messages (about 2.5 GiB) through the HOST batch calls
+    (snb_compress_batch / snb_uncompress_batch, packed output).  Oracle compare on a seeded 20 000-message sample
+    (byte for byte, snappy.nim:27-64 per message) + full round trip of all 1 M on the GPU path."""
+    import time
+    from nim_snappy_b200.workloads import message_batch
+    count = 1_000_000
+    packed, offs, lens = message_batch(count, seed=0)
+    t0 = time.perf_counter()
+    out, out_len, status = gpu_api.compressBatch(packed, offs, lens)
+    t_c = time.perf_counter() - t0
+    assert not status.any()
+    ends = np.cumsum(out_len, dtype=np.uint64)
+    rng = np.random.default_rng(1)
+    sample = np.concatenate([rng.choice(count, size=19990, replace=False), np.arange(5), np.arange(count - 5, count)])
+    for i in sample:
+        exp = oracle.encode(packed[offs[i]:offs[i] + lens[i]])
+        e = int(ends[i])
+        assert out_len[i] == len(exp) and out[e - len(exp):e].tobytes() == exp, int(i)
+    total = int(ends[-1])
+    t0 = time.perf_counter()
+    back, back_len, st2 = gpu_api.uncompressBatch(out[:total], ends - out_len, out_len)
+    t_d = time.perf_counter() - t0
+    assert not st2.any() and np.array_equal(back_len, lens.astype(np.uint32))
+    assert back.size == packed.size and np.array_equal(back, packed)
+    print(f"config 4 through host (pageable) buffers: compress {packed.size / t_c / 1e9:.2f} GB/s, "
+          f"uncompress {packed.size / t_d / 1e9:.2f} GB/s, ratio {total / packed.size:.3f}")
+
+
+def test_config5_mixed_8gib_slab_loop(dc, oracle):
+    """BASELINE configs[4] on one GPU: 8 GiB of the mixed corpus (text | protobuf-like | random per MiB) through the
+    device slab loop (8 slabs of 16 384 chunks).  Sampled oracle compare of whole frames at every slab boundary and at
+    random chunks (frame bytes, CRC and placement), stream size == 10 + sum of the frame lengths, full GPU round trip."""
+    import torch
+    from nim_snappy_b200.workloads import mixed_corpus
+    gib, slabs = 1 << 30, 8
+    d_in = torch.empty(slabs * gib, dtype=torch.uint8, device="cuda")
+    host = {}
+    for k in range(slabs):                                  # every slab different: seed and phase move with k
+        h = mixed_corpus(gib, seed=100 + k, phase_mib=k)
+        d_in[k * gib:(k + 1) * gib] = torch.from_numpy(h).cuda()
+        if k in (0, 3, 7):
+            host[k] = h
+        else:
+            host[k] = np.concatenate([h[:3 * 65536], h[-3 * 65536:]])      # the chunks next to the slab boundaries
+    n = slabs * gib
+    nchunks = n // 65536
+    lens = torch.zeros(nchunks, dtype=torch.int32, device="cuda")
+    out, w = dc.compress_framed(d_in, frame_lens=lens)
+    fl = lens.cpu().numpy().astype(np.int64)
+    assert w == 10 + int(fl.sum())
+    starts = 10 + np.concatenate([[0], np.cumsum(fl)[:-1]])
+    rng = np.random.default_rng(7)
+    sample = set()
+    for k in range(slabs):
+        sample.update(range(k * 16384, k * 16384 + 3))
+        sample.update(range((k + 1) * 16384 - 3, (k + 1) * 16384))
+    for k in (0, 3, 7):
+        sample.update(int(k * 16384 + c) for c in rng.integers(0, 16384, 400))
+    for c in sorted(sample):
+        k, j = divmod(c, 16384)
+        h = host[k]
+        if h.size == gib:
+            chunk = h[j * 65536:(j + 1) * 65536]
+        else:
+            chunk = h[j * 65536:(j + 1) * 65536] if j < 3 else h[(j - 16384 + 6) * 65536:(j - 16384 + 7) * 65536]
+        exp = oracle.encode_framed(chunk)[10:]                 # one frame: header, masked CRC, payload
+        got = out[int(starts[c]):int(starts[c]) + int(fl[c])].cpu().numpy().tobytes()
+        assert got == exp, c
+    # full round trip on the device path (header walk of the host copy of the stream; see snb_dev_uncompress_framed)
+    stream_h = out[:w].cpu().numpy()
+    chunks, walk = dc.frame_index(stream_h)
+    assert len(chunks) == nchunks and walk.status == 0 and walk.written == n
+    d_back = torch.empty(n, dtype=torch.uint8, device="cuda")
+    status = dc.uncompress_chunks(out[:w], chunks, d_back)
+    assert not status.any()
+    for k in range(slabs):
+        assert bool((d_back[k * gib:(k + 1) * gib] == d_in[k * gib:(k + 1) * gib]).all()), k
+
+
+def test_device_side_header_walk(dc, gpu_api, oracle):
+    """snb_dev_frame_index / snb_dev_uncompress_framed: the framed header walk on the device."""
+    import torch
+    from nim_snappy_b200.workloads import mixed_corpus, text_corpus
+    rng = np.random.default_rng(23)
+    alice = read_data("alice29.txt")
+    datas = [b"", b"abc", alice, read_data("house.jpg") + read_data("html"), bytes(200000),
+             mixed_corpus(5 << 20, seed=3).tobytes()]
+    P.check_dev_framed(P.gpu_dev_call(dc), oracle, datas, rng, fuzz=40, lib=gpu_api.lib)
+    # the stream a device-resident caller has: produced by snb_dev_compress_framed, never on the host
+    d = text_corpus(256 << 20)
+    d_in = torch.from_numpy(d).cuda()
+    lens = torch.zeros(d.size // 65536, dtype=torch.int32, device="cuda")
+    out, n = dc.compress_framed(d_in, frame_lens=lens)
+    d_back = torch.zeros(d.size, dtype=torch.uint8, device="cuda")
+    f0 = gpu_api.lib.snb_frame_index_fallbacks()
+    for fl in (None, lens):
+        d_back.zero_()
+        assert dc.uncompress_framed(out[:n], d_back, frame_lens=fl) == (0, n, d.size)
+        assert bool((d_back == d_in).all())
+    d_chunks, walk = dc.dev_frame_index(out[:n])
+    h_chunks, hwalk = dc.frame_index(out[:n].cpu().numpy())
+    assert (walk.status, walk.read, walk.written) == (hwalk.status, hwalk.read, hwalk.written)
+    assert d_chunks.cpu().numpy().tobytes() == h_chunks.tobytes()          # the same descriptors as the host walk
+    assert gpu_api.lib.snb_frame_index_fallbacks() == f0
+    bad = out[:n].clone()
+    bad[int(h_chunks[2000]["in_off"]) + 50] ^= 1                           # payload damage: that chunk's CRC / tags fail
+    st, rd, wr = dc.uncompress_framed(bad, d_back)
+    assert st in (2, 3) and rd == int(h_chunks[2000]["in_off"]) - 8 and wr == 2000 * 65536
+    bad = out[:n].clone()
+    bad[int(h_chunks[3000]["in_off"]) - 8] = 0x7f                          # header damage: unknownChunk after 3000 chunks
+    ref = oracle.uncompress_framed(bad.cpu().numpy().tobytes(), d.size)
+    assert dc.uncompress_framed(bad, d_back)[0] == ref[0] == 4
+
+
+def test_concurrent_callers_and_streams(gpu_api, dc, oracle):
+    """Four host threads call snb_compress_framed / snb_uncompress_framed / the batch calls at once while a fifth
+    issues snb_dev_* calls without synchronising on two different CUDA streams: every result byte-exact (the library
+    serialises the host calls and orders the device calls' use of its shared work buffers across streams)."""
+    import threading
+    import torch
+    from nim_snappy_b200.workloads import mixed_corpus, text_corpus
+    datas = [text_corpus(20 << 20, phase=i * 1000).tobytes() for i in range(2)] + [mixed_corpus(12 << 20, seed=i).tobytes() for i in range(2)]
+    expect = [oracle.encode_framed(d) for d in datas]
+    errors = []
+
+    def host_worker(i):
+        try:
+            for _ in range(4):
+                assert gpu_api.encodeFramed(datas[i]) == expect[i]
+                assert gpu_api.decodeFramed(expect[i]) == datas[i]
+                msgs = [datas[i][k * 3000:(k + 1) * 3000] for k in range(50)]
+                assert gpu_api.encodeBatch(msgs) == [oracle.encode(m) for m in msgs]
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    def dev_worker():
+        try:
+            streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+            d_ins = [torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda() for d in datas]
+            outs = [torch.empty(oracle.max_compressed_len_framed(len(d)), dtype=torch.uint8, device="cuda") for d in datas]
+            torch.cuda.synchronize()
+            for rep in range(6):
+                counts = []
+                for j in range(len(datas)):
+                    with torch.cuda.stream(streams[(j + rep) & 1]):
+                        counts.append(dc.compress_framed(d_ins[j], out=outs[j], sync=False)[1])   # no host sync between calls
+                torch.cuda.synchronize()
+                for j in range(len(datas)):
+                    n = int(counts[j].item())
+                    assert n == len(expect[j]) and outs[j][:n].cpu().numpy().tobytes() == expect[j], (rep, j)
+        except Exception as e:  # noqa: BLE001
+            errors.append(("dev", repr(e)))
+
+    ts = [threading.Thread(target=host_worker, args=(i,)) for i in range(4)] + [threading.Thread(target=dev_worker)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
