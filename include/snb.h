@@ -199,11 +199,9 @@ uint64_t snb_frame_index_fallbacks(void);
 uint64_t snb_debug_kernel_span_ns(void);
 /* Tuning: warps per CTA of the compress kernel for 64 KiB blocks (hash tables are 32 KiB each). */
 void snb_set_compress_warps(int warps);
-/* Tuning / A-B testing of the block encoder: 0 = auto (default: one thread per block with tables in HBM for
- * batches of at least `thread_min_chunks` blocks, window-resolve warps otherwise), 1 = per-step warp encoder,
- * 2 = window-resolve warp encoder, 3 = one thread per block. */
+/* A-B testing of the block encoder for 64 KiB chunks: 0 / 5 = one warp per chunk (default), 6 = resolver warps + walker
+ * warp per chunk with every hash table in shared memory (experimental: byte-identical, slower). */
 void snb_set_compress_algo(int algo);
-void snb_set_thread_min_chunks(int n);
 /* How long the streaming compress kernel waits for a chunk whose host-to-device copy has not landed (default 2000 ms;
  * then the call returns SNB_TIMEOUT instead of hanging). */
 void snb_set_arrive_timeout_ms(int ms);

@@ -67,7 +67,6 @@ SIGNATURES = {
     "snb_debug_kernel_span_ns": (_u64, []),
     "snb_set_compress_warps": (None, [_i]),
     "snb_set_compress_algo": (None, [_i]),
-    "snb_set_thread_min_chunks": (None, [_i]),
     "snb_set_arrive_timeout_ms": (None, [_i]),
 }
 

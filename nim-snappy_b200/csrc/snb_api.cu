@@ -104,13 +104,15 @@ struct Ctx {
   uint32_t call_launches = 0;
   int compress_warps = 4;    // 64 KiB blocks: encoder warps per SM with the table in shared memory (more would squeeze the L1 below what the candidate loads need)
   int compress_gwarps = 18;  // ... and with the table in global memory (L2); 18 measured best on text (round 1f sweep), 20 on mixed data
-  int compress_algo = 0;  // 0 auto (= 5), 1/2/4/5 warp encoders v1/v2/v3/v5, 3 one thread per block
+  int compress_algo = 0;  // 0 auto (= 5: one warp per chunk, window walk on ballot masks), 6: resolver / walker warp groups (experimental)
   size_t l2_persist_max = 0, l2_window_max = 0;   // device limits for the L2 access-policy window (0: unsupported)
-  int l2_tables = 1;                              // keep the encoder's global-memory hash tables resident in L2
+  int l2_tables = 0;                              // 1: persisting-L2 carve-out + access-policy window for the encoder's global-memory hash tables.
+                                                  // Off by default: measured neutral outside a profiler (23.5 vs 23.8 ms / GiB), and under ncu the window is
+                                                  // not applied while the carve-out still takes its share of the L2 -- the kernel then runs at HALF speed
+                                                  // (47 vs 23.7 ms; profiles/r2_ncu_bisect.log), i.e. every capture described a different kernel.
   float l2_ratio = 0.f;                           // 0: derive from the carve-out and the table bytes
   uint32_t dec_slab_chunks = 1024;  // host decode pipeline: chunks per H2D | kernel | D2H slab (64 MiB of output: short fill / drain)
   int arrive_timeout_ms = 2000;     // streaming compress: a chunk whose input has not landed after this long ends the call with SNB_TIMEOUT
-  int thread_min_chunks = 1 << 30;  // auto mode: batches at least this large use one thread per block (tables in HBM)
   std::string err;
 };
 Ctx g;
@@ -251,7 +253,6 @@ int do_init(int device) {
   CK(cudaEventCreateWithFlags(&g.ev_reset, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g.ev_dev, cudaEventDisableTiming));
   CK(cudaFuncSetAttribute(snb::compress_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CK(cudaFuncSetAttribute(snb::compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(snb::compress_kernel5, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(snb::compress_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #ifndef SNB_EMULATE
@@ -310,7 +311,6 @@ void prof_collect(int first_pair, int n_pairs, int slot0) {
 
 // ---------------------------------------------------------------- launch geometry
 struct CompressGeom { uint32_t entries, warps, smem_warps, grid; size_t smem; };
-bool use_v5() { return g.compress_algo == 0 || g.compress_algo == 5 || g.compress_algo == 6; }   // the streaming (one launch per slab) path
 bool use_pipe() { return g.compress_algo == 6; }   // ... with the resolver / walker kernel (v6): byte-exact, 2x algorithmic DRAM traffic, but 20 GB/s (walker-latency bound) -- not the default
 CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
   CompressGeom cg;
@@ -318,9 +318,8 @@ CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
   while (e < snb::kMaxTableEntries && e < max_len) e <<= 1;
   cg.entries = e;
   const size_t tbytes = (size_t)e * 2;
-  const bool v5 = use_v5();
-  const uint32_t max_warps = (v5 ? snb::kCompress5MaxThreads : snb::kCompressMaxThreads) / 32;
-  const size_t stage = v5 ? 0 : (size_t)snb::kStageWords * 4;   // per-warp staging area of the v3 encoder
+  const uint32_t max_warps = snb::kCompress5MaxThreads / 32;
+  const size_t stage = 0;
   uint32_t ctas_per_sm;
   if (e == snb::kMaxTableEntries) {
     // 7 x 32 KiB tables fill the shared memory of an SM; further warps keep their table in L2
@@ -339,8 +338,7 @@ CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
   return cg;
 }
 void launch_compress(const snb::CompressArgs& a, const CompressGeom& cg, cudaStream_t st) {
-  if (use_v5()) SNB_LAUNCH(snb::compress_kernel5, cg.grid, cg.warps * 32, cg.smem, st, a);
-  else SNB_LAUNCH(snb::compress_kernel, cg.grid, cg.warps * 32, cg.smem, st, a);
+  SNB_LAUNCH(snb::compress_kernel5, cg.grid, cg.warps * 32, cg.smem, st, a);
 }
 
 // ---------------------------------------------------------------- device-side building blocks
@@ -356,81 +354,9 @@ int launch_crc(const uint8_t* base, const uint64_t* off, const uint32_t* len, ui
   return SNB_OK;
 }
 
-// Compress the 64 KiB blocks of a contiguous device buffer and pack the results back to back
-// at d_dst + dst_base.  mode: kModeFrame (encodeFrame per block) or kModeRawBlock.
-// d_total[0] receives the end offset (dst_base + bytes produced).
-int dev_compress_contig(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t* d_dst, uint64_t dst_base,
-                        uint32_t* d_frame_lens, cudaStream_t st) {
-  uint64_t count64 = (n + kChunk - 1) / kChunk;
-  if (count64 == 0) {
-    CK(cudaMemcpyAsync(g.d_total, &dst_base, 8, cudaMemcpyHostToDevice, st));
-    return SNB_OK;
-  }
-  uint32_t slab = (uint32_t)std::min<uint64_t>(count64, kDevSlabChunks);
-  const uint64_t kSlotStride = mode == snb::kModeFrame ? kFrameStride : kRawStride;
-  CK(g.scratch.ensure((size_t)slab * kSlotStride + 4096));
-  CK(g.lens.ensure((size_t)slab * 4));
-  CK(g.offs.ensure((size_t)slab * 8));
-  CK(g.crcs.ensure((size_t)slab * 4));
-  for (uint64_t first = 0; first < count64; first += slab) {
-    uint32_t cnt = (uint32_t)std::min<uint64_t>(slab, count64 - first);
-    const uint8_t* sin = d_in + first * kChunk;
-    uint64_t slen = std::min<uint64_t>(n - first * kChunk, (uint64_t)cnt * kChunk);
-    bool p = g.profiling && first == 0;
-    if (mode == snb::kModeFrame) {
-      if (p) prof_mark(0, st);
-      CKS(launch_crc(sin, nullptr, nullptr, slen, cnt, g.crcs.as<uint32_t>(), 1, st));
-      if (p) prof_mark(1, st);
-    }
-    if (g.compress_algo == 3 || (g.compress_algo == 0 && cnt >= (uint32_t)g.thread_min_chunks)) {
-      // one thread per block, hash tables in global memory
-      CK(g.tables.ensure((size_t)cnt * snb::kMaxTableEntries * 2));
-      CK(cudaMemsetAsync(g.tables.p, 0, (size_t)cnt * snb::kMaxTableEntries * 2, st));
-      snb::CompressTArgs t;
-      t.in_base = sin; t.out_base = g.scratch.as<uint8_t>(); t.tables = g.tables.as<uint16_t>(); t.total_len = slen;
-      t.out_stride = kSlotStride; t.crc = g.crcs.as<uint32_t>(); t.out_len = g.lens.as<uint32_t>(); t.count = cnt;
-      t.mode = mode;
-      if (p) prof_mark(2, st);
-      SNB_LAUNCH(snb::compress_thread_kernel, (cnt + 31) / 32, 32, 0, st, t);
-    } else {
-      snb::CompressArgs a;
-      a.in_base = sin; a.out_base = g.scratch.as<uint8_t>(); a.in_off = nullptr; a.in_len = nullptr; a.out_off = nullptr;
-      a.total_len = slen; a.out_stride = kSlotStride; a.crc = g.crcs.as<uint32_t>(); a.out_len = g.lens.as<uint32_t>();
-      a.count = cnt; a.mode = mode;
-      CKS(next_counter(st, &a.counter));
-      CompressGeom cg = compress_geom((uint32_t)kChunk, cnt);
-      a.table_entries = cg.entries;
-      a.smem_warps = cg.smem_warps;
-      CK(g.tables.ensure((size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2 + 256));
-      a.gtables = g.tables.as<uint16_t>();
-      a.algo = (uint32_t)((g.compress_algo == 1 || g.compress_algo == 2) ? g.compress_algo : 4);
-      a.defer_stored = mode == snb::kModeFrame ? 1u : 0u;
-      if (p) prof_mark(2, st);
-      launch_compress(a, cg, st);
-    }
-    count_launch();
-    CK(cudaGetLastError());
-    if (p) { prof_mark(3, st); prof_mark(4, st); }
-    SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, st, g.lens.as<uint32_t>(), g.offs.as<uint64_t>(), cnt,
-               first == 0 ? (const uint64_t*)nullptr : (const uint64_t*)g.d_total, first == 0 ? dst_base : 0ull,
-               g.d_total);
-    count_launch();
-    CK(cudaGetLastError());
-    if (p) { prof_mark(5, st); prof_mark(6, st); }
-    uint32_t cgrid = std::max(1u, std::min(cnt, (uint32_t)g.sms * 8));
-    SNB_LAUNCH(snb::compact_kernel, cgrid, 256, 0, st, g.scratch.as<uint8_t>(), kSlotStride, g.lens.as<uint32_t>(),
-               g.offs.as<uint64_t>(), d_dst, cnt, mode == snb::kModeFrame ? sin : (const uint8_t*)nullptr);
-    count_launch();
-    CK(cudaGetLastError());
-    if (p) prof_mark(7, st);
-    if (d_frame_lens)
-      CK(cudaMemcpyAsync(d_frame_lens + first, g.lens.p, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, st));
-  }
-  return SNB_OK;
-}
-
-// The same job as dev_compress_contig in ONE persistent kernel per slab (compress_stream_kernel: CRC, encode,
-// in-order packing).  d_arrived (optional) lets the kernel start while the input is still being copied in;
+// Compress the 64 KiB blocks of a contiguous device buffer and pack the results back to back at d_dst + dst_base, in
+// ONE persistent kernel per slab (compress_stream_kernel: CRC, encode, in-order packing).  mode: kModeFrame
+// (encodeFrame per block) or kModeRawBlock.  d_arrived (optional) lets the kernel start while the input is still being copied in;
 // h_flags (optional, host-mapped, one word per group of kGroupChunks chunks over the whole call) receives
 // each group's end offset + 1 as soon as the group is packed.  chunk0: index of d_in's first chunk in
 // d_arrived's units.  d_total[0] receives the end offset.
@@ -470,7 +396,7 @@ int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
     a.c.count = cnt; a.c.mode = mode;
     CKS(next_counter(st, &a.c.counter));
     a.c.table_entries = cg.entries; a.c.smem_warps = cg.smem_warps; a.c.gtables = g.tables.as<uint16_t>();
-    a.c.algo = 5; a.c.defer_stored = mode == snb::kModeFrame ? 1u : 0u;
+    a.c.defer_stored = mode == snb::kModeFrame ? 1u : 0u;
     a.dst = d_dst; a.frontier = d_total + 1; a.arrived = d_arrived;
     a.group_done = g.group_done.as<uint32_t>(); a.group_end = g.group_end.as<unsigned long long>();
     a.host_flags = h_flags ? h_flags + first / kGroupChunks : nullptr;
@@ -567,21 +493,6 @@ int wait_group_flag(volatile unsigned long long* flag, cudaEvent_t kernel_done, 
 
 int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, uint32_t mode) {
   if (n == 0) return SNB_OK;
-  if (!use_v5()) {  // the older encoders keep the plain slab pipeline
-    const uint64_t count = (n + kChunk - 1) / kChunk;
-    const size_t per_block = mode == snb::kModeFrame ? (size_t)(kChunk + 8) : (size_t)SNB_MAX_COMPRESSED_FRAME_LEN;
-    CK(g.in[0].ensure(n + 64));
-    CK(g.out[0].ensure(count * per_block + 65536));
-    CK(g.h_meta[0].ensure(64));
-    CK(cudaMemcpyAsync(g.in[0].p, in, n, cudaMemcpyHostToDevice, g.s0));
-    CKS(dev_compress_contig(g.in[0].as<uint8_t>(), n, mode, g.out[0].as<uint8_t>(), 0, nullptr, g.s0));
-    CK(cudaMemcpyAsync(g.h_meta[0].p, g.d_total, 8, cudaMemcpyDeviceToHost, g.s0));
-    CK(cudaStreamSynchronize(g.s0));
-    const uint64_t total = *g.h_meta[0].as<uint64_t>();
-    CK(cudaMemcpy(out + *pos, g.out[0].p, total, cudaMemcpyDeviceToHost));
-    *pos += total;
-    return SNB_OK;
-  }
   const bool dbg_e2e = getenv("SNB_DEBUG_E2E") != nullptr;   // host-side timeline of the streaming pipeline on stderr
   const auto t_begin = std::chrono::steady_clock::now();
   const uint64_t slab_bytes = (uint64_t)kDevSlabChunks * kChunk;
@@ -1057,6 +968,7 @@ int dev_frame_index(const uint8_t* d_stream, uint64_t n, uint64_t out_cap, int c
     CK(cudaMemcpyAsync((uint8_t*)hs + 128, d_tot, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     n_cand = (size_t)*(unsigned long long*)((uint8_t*)hs + 128);
+    if (getenv("SNB_DEBUG_INDEX")) fprintf(stderr, "frame index scan: n=%llu blocks=%u cand=%zu overflow=%u\n", (unsigned long long)n, nblocks, n_cand, hs->overflow);
     if (hs->overflow || n_cand == 0 || n_cand > cand_limit) return fallback();
     CKS(carve(n_cand + 1));
     SNB_LAUNCH(gather_kernel, nblocks, 256, 0, st, a); count_launch();
@@ -1252,7 +1164,7 @@ int host_compress_batch(const uint8_t* in_base, const uint64_t* in_off, const ui
     CKS(next_counter(sc, &a.counter));
     CompressGeom cgs = compress_geom(std::max(1u, max_len), (uint32_t)cnt);
     a.table_entries = cgs.entries; a.smem_warps = cgs.smem_warps; a.gtables = g.tables.as<uint16_t>();
-    a.algo = 4; a.defer_stored = 0;
+    a.defer_stored = 0;
     SNB_LAUNCH(snb::compress_kernel5, cgs.grid, cgs.warps * 32, cgs.smem, sc, a); count_launch();
     CK(cudaGetLastError());
     SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, sc, d_olen, d_offs, (uint32_t)cnt, (const uint64_t*)nullptr, 0ull, g.d_total + 2);
@@ -1569,8 +1481,7 @@ int snb_dev_compress_framed(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uin
   if (n == 0) {
     CK(cudaMemcpyAsync(g.d_total, &base, 8, cudaMemcpyHostToDevice, st));
   } else {
-    if (use_v5()) CKS(dev_compress_stream(d_in, n, snb::kModeFrame, d_out, base, d_frame_lens, st, nullptr, 0, nullptr));
-    else CKS(dev_compress_contig(d_in, n, snb::kModeFrame, d_out, base, d_frame_lens, st));
+    CKS(dev_compress_stream(d_in, n, snb::kModeFrame, d_out, base, d_frame_lens, st, nullptr, 0, nullptr));
   }
   if (d_written) CK(cudaMemcpyAsync(d_written, g.d_total, 8, cudaMemcpyDeviceToDevice, st));
   CKS(dev_end(st));
@@ -1579,7 +1490,7 @@ int snb_dev_compress_framed(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uin
     CK(cudaMemcpyAsync(g.h_meta[0].p, g.d_total, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (written) *written = *g.h_meta[0].as<uint64_t>();
-    if (n) { if (use_v5()) prof_collect(2, 1, 1); else prof_collect(0, 4, 0); }
+    if (n) prof_collect(2, 1, 1);
     g.prof[5] = (float)g.call_launches;
   }
   return SNB_OK;
@@ -1691,7 +1602,6 @@ int snb_dev_compress_batch(const uint8_t* d_in, const uint64_t* d_in_off, const 
   a.smem_warps = cg.smem_warps;
   CK(g.tables.ensure((size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2 + 256));
   a.gtables = g.tables.as<uint16_t>();
-  a.algo = (uint32_t)((g.compress_algo == 1 || g.compress_algo == 2) ? g.compress_algo : 4);
   a.defer_stored = 0;
   prof_mark(2, st);
   launch_compress(a, cg, st);
@@ -1796,7 +1706,6 @@ uint64_t snb_debug_kernel_span_ns(void) {
 void snb_set_compress_warps(int warps) { std::lock_guard<std::mutex> lk(g_mu); g.compress_warps = warps % 100; if (warps >= 100) g.compress_gwarps = warps / 100 - 1; }
 void snb_set_compress_algo(int algo) { std::lock_guard<std::mutex> lk(g_mu); g.compress_algo = algo; }
 void snb_set_arrive_timeout_ms(int ms) { std::lock_guard<std::mutex> lk(g_mu); g.arrive_timeout_ms = ms; }
-void snb_set_thread_min_chunks(int n) { std::lock_guard<std::mutex> lk(g_mu); g.thread_min_chunks = n; }
 
 // Page-locked host memory for callers that stream through the host-buffer entry points: pinned buffers are
 // DMA'd directly by snb_compress* / snb_uncompress* (is_pinned), pageable ones go through the driver's staging.

@@ -5,7 +5,9 @@
 //
 // What each routine reproduces (reference file:line, /root/reference @ 8ab5cf0):
 //   crc32c_warp          snappy/crc32c.c:204-214,676-763 + snappy/codec.nim:71-75 (maskedCrc)
-//   compress_block_warp  snappy/encoder.nim:184-383 (encodeBlock), :44-73, :81-125, :130-182
+//   compress_block_v5    snappy/encoder.nim:184-383 (encodeBlock), :44-73, :81-125, :130-182
+//   compress_block_v6    the same parse split over resolver warps and a walker warp (snb_pipe.cuh, experimental)
+//   fidx::*              snappy.nim:199-265 header walk on the device (snb_frameidx.cuh)
 //   compress_job         snappy/encoder.nim:385-426 (encodeFrame) / snappy.nim:27-64 (compress)
 //   decompress_warp      snappy.nim:84-110 (uncompress) + snappy/decoder.nim:20-155 (decodeAllTags)
 //
@@ -62,21 +64,6 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) {
 #endif
 // index of the lowest non-zero byte of x (x != 0)
 __device__ __forceinline__ uint32_t first_diff_byte(uint32_t x) { return (uint32_t)(__ffs((int)x) - 1) >> 3; }
-// Asynchronous 4-byte global -> shared copies (LDGSTS): completion is tracked per commit group, not by a
-// register scoreboard, so a copy issued in one pass of a long loop can be consumed a pass later without
-// the consumer also waiting for younger loads that happen to share a scoreboard slot.
-#ifdef SNB_EMULATE
-__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) { *smem_dst = *gsrc; }
-__device__ __forceinline__ void cp_async_commit() {}
-__device__ __forceinline__ void cp_async_wait_all() {}
-#else
-__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-#endif
 // Cache hints (no destination register, no scoreboard): bring the line holding p towards the SM.
 #ifdef SNB_EMULATE
 __device__ __forceinline__ void prefetch_l1(const void*) {}
@@ -101,14 +88,6 @@ __device__ __forceinline__ uint32_t load32u(const uint8_t* p) {
   uint32_t hi = sh ? w[1] : 0u;
   return __funnelshift_r(lo, hi, sh);
 }
-// Up to k (0..4) bytes, zero filled.
-__device__ __forceinline__ uint32_t load_upto4(const uint8_t* p, uint32_t k) {
-  if (k >= 4) return load32u(p);
-  uint32_t v = 0;
-  for (uint32_t i = 0; i < k; i++) v |= (uint32_t)p[i] << (8 * i);
-  return v;
-}
-
 // Cooperative byte copy, any alignment, non-overlapping.  dst-aligned 32-bit stores.
 __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) {
   if (n < 64) {
@@ -212,45 +191,8 @@ __device__ __forceinline__ uint32_t hash14(uint32_t d, uint32_t mask) {  // enco
   return ((d * 0x1e35a7bdu) >> 18) & mask;
 }
 
-// Length of the common prefix of in[s1..] and in[s2..] (s1 < s2), the s2 side bounded by len.
-// encoder.nim:130-182.  Lane j compares bytes [4j, 4j+4) of each 128-byte step.  Uniform result.
-__device__ __forceinline__ uint32_t common_prefix_warp(const uint8_t* in, uint32_t len, uint32_t s1, uint32_t s2,
-                                                       uint32_t lane) {
-  uint32_t matched = 0;
-  for (;;) {
-    uint32_t o = 4 * lane;
-    uint32_t rem = len - s2;  // bytes left on the s2 side (may be 0)
-    uint32_t nv = rem > o ? umin32(rem - o, 4) : 0;
-    uint32_t x;
-    if (nv == 4) {
-      x = load32u(in + s1 + o) ^ load32u(in + s2 + o);
-    } else {
-      x = 0;
-      for (uint32_t i = 0; i < nv; i++) x |= (uint32_t)(in[s1 + o + i] ^ in[s2 + o + i]) << (8 * i);
-      x |= 1u << (8 * nv);  // sentinel: first byte past the end never matches
-    }
-    uint32_t mism = __ballot_sync(kFull, x != 0);
-    if (mism) {
-      int l = __ffs((int)mism) - 1;
-      uint32_t xl = __shfl_sync(kFull, x, l);
-      return matched + 4 * (uint32_t)l + ((uint32_t)(__ffs((int)xl) - 1) >> 3);
-    }
-    matched += 128; s1 += 128; s2 += 128;
-  }
-}
-
 // Encoded size of an n-byte literal (tag + length bytes + payload), encoder.nim:57-73.
 __device__ __forceinline__ uint32_t literal_size(uint32_t n) { return n + (n <= 60 ? 1 : n <= 256 ? 2 : 3); }
-
-// encoder.nim:44-73.  Returns bytes written (uniform).
-__device__ __forceinline__ uint32_t emit_literal_warp(uint8_t* o, const uint8_t* s, uint32_t n, uint32_t lane) {
-  uint32_t m = (n - 1) & 0xffff, w;
-  if (m < 60) { w = 1; if (lane == 0) o[0] = (uint8_t)(m << 2); }
-  else if (m < 256) { w = 2; if (lane == 0) { o[0] = 60 << 2; o[1] = (uint8_t)m; } }
-  else { w = 3; if (lane == 0) { o[0] = 61 << 2; o[1] = (uint8_t)m; o[2] = (uint8_t)(m >> 8); } }
-  warp_copy(o + w, s, n, lane);
-  return w + n;
-}
 
 // encoder.nim:81-125.  Returns bytes written (uniform).
 __device__ __forceinline__ uint32_t emit_copy_warp(uint8_t* o, uint32_t off, uint32_t len, uint32_t lane) {
@@ -274,136 +216,7 @@ __device__ __forceinline__ uint32_t emit_copy_warp(uint8_t* o, uint32_t off, uin
   return w + 2;
 }
 
-// encodeBlock (encoder.nim:184-383), one warp, hash table `table` (>= tableSize(len) u16
-// entries of shared memory).  Returns the encoded length, or kAborted as soon as the output
-// exceeds abort_thr (encodeFrame's blockLen <= len - len/8 test, encoder.nim:408, decided early:
-// op only grows).  `out` needs abort_thr + 3100 bytes (frames) or 32+len+len/6 (raw).
-//
-// Literal scan: the probe positions of a run are a pure function of the run start
-// (encoder.nim:281-331), so 32 probes are hashed, looked up and compared at once; same-window
-// hash collisions are resolved to "latest earlier lane" with match.any, and only the probes up
-// to the winning one commit their table insert (last writer wins), which is exactly the table
-// state the serial loop leaves behind.
-__device__ __forceinline__ uint32_t compress_block_warp(const uint8_t* __restrict__ in, uint32_t len,
-                                                        uint8_t* __restrict__ out, uint16_t* table,
-                                                        uint32_t abort_thr, uint32_t lane) {
-  if (len < kMinNonLiteral) return emit_literal_warp(out, in, len, lane);  // :227-229
-
-  uint32_t tsize = 256;  // :27-34
-  while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
-  const uint32_t mask = tsize - 1;
-  {
-    uint32_t* t32 = (uint32_t*)table;
-    for (uint32_t i = lane; i < tsize / 2; i += 32) t32[i] = 0;
-  }
-  const uint32_t ip_limit = len - kInputMargin;  // :245
-  uint32_t ip = 0, op = 0;
-
-  for (;;) {
-    uint32_t next_emit = ip;
-    ip += 1;
-    uint32_t cand = 0;
-    bool off_end = false;
-
-    // ---------------- literal scan, 32 probes per step (:281-331)
-    uint32_t wip = ip, wskip = 32;
-    bool first = true;
-    for (;;) {
-      __syncwarp();  // table writes of the previous step / copy loop are visible
-      uint32_t p, step, sk_after;
-      if (first) {  // stride 1 for the first 32 probes whichever way the run starts
-        p = wip + lane; step = 1; sk_after = 64;
-      } else {
-        uint32_t pos = wip, sk = wskip;
-        for (uint32_t j = 0; j < lane; j++) { uint32_t st = sk >> 5; sk += st; pos += st; }
-        p = pos; step = sk >> 5; sk_after = sk + step;
-      }
-      // :318-321 -- a probe happens only if the next position stays within ip_limit
-      bool valid = (p <= ip_limit) && (p + step <= ip_limit);
-      uint32_t d = 0, h = 0x10000u + lane, tv = 0;
-      if (valid) { d = load32u(in + p); h = hash14(d, mask); tv = table[h]; }
-      uint32_t grp = __match_any_sync(kFull, h);
-      uint32_t earlier = grp & ((1u << lane) - 1u);
-      int src = earlier ? 31 - __clz((int)earlier) : (int)lane;
-      uint32_t pe = __shfl_sync(kFull, p, src);
-      uint32_t c = earlier ? pe : tv;
-      bool hit = valid && (load32u(in + c) == d);
-      uint32_t hitmask = __ballot_sync(kFull, hit);
-      uint32_t vmask = __ballot_sync(kFull, valid);
-      if (hitmask) {
-        int kh = __ffs((int)hitmask) - 1;
-        uint32_t commit = (2u << kh) - 1u;
-        uint32_t cg = grp & commit;
-        if (((commit >> lane) & 1u) && (cg >> lane) == 1u) table[h] = (uint16_t)p;
-        ip = __shfl_sync(kFull, p, kh);
-        cand = __shfl_sync(kFull, c, kh);
-        break;
-      }
-      if (vmask != kFull) { off_end = true; break; }
-      if ((grp >> lane) == 1u) table[h] = (uint16_t)p;
-      wip = __shfl_sync(kFull, p + step, 31);
-      wskip = __shfl_sync(kFull, sk_after, 31);
-      first = false;
-    }
-
-    if (off_end) {  // :319-321 -> emitRemainder from next_emit
-      uint32_t n = len - next_emit;
-      if (op + literal_size(n) > abort_thr) return kAborted;
-      return op + emit_literal_warp(out + op, in + next_emit, n, lane);
-    }
-
-    {  // :336-338
-      uint32_t n = ip - next_emit;
-      if (op + literal_size(n) > abort_thr) return kAborted;
-      op += emit_literal_warp(out + op, in + next_emit, n, lane);
-    }
-
-    // ---------------- copy loop (:350-380)
-    uint32_t matched = 4 + common_prefix_warp(in, len, cand + 4, ip + 4, lane);
-    for (;;) {
-      op += emit_copy_warp(out + op, ip - cand, matched, lane);
-      ip += matched;
-      if (op > abort_thr) return kAborted;
-      if (ip > ip_limit) {  // :362-363
-        if (ip < len) {
-          uint32_t n = len - ip;
-          if (op + literal_size(n) > abort_thr) return kAborted;
-          op += emit_literal_warp(out + op, in + ip, n, lane);
-        }
-        return op;
-      }
-      __syncwarp();
-      uint32_t d1 = load32u(in + ip - 1), d = load32u(in + ip);
-      uint32_t h1 = hash14(d1, mask), h = hash14(d, mask);
-      uint32_t tv = table[h];
-      cand = (h == h1) ? ip - 1 : tv;  // :371-377: insert ip-1, then look up / insert ip
-      __syncwarp();                    // every lane has read before lane 0 writes
-      if (lane == 0) { table[h1] = (uint16_t)(ip - 1); table[h] = (uint16_t)ip; }
-      matched = common_prefix_warp(in, len, cand, ip, lane);
-      if (matched < 4) break;          // :379-380
-    }
-  }
-}
-
-// --------------------------------------------------------------------- encodeBlock, v2
-// Same byte-exact parse as compress_block_warp, organised around 32-position windows so that
-// the expensive work is done once per window instead of once per parse step:
-//
-//   phase A (wide): lane l owns position b+l: 8 input bytes, hash, table entry T as of the
-//            window start, 8 candidate bytes, match length ml (0..8) against T, and the
-//            match.any group of its hash.
-//   phase B (uniform): the greedy parse walks the window using those per-lane results through
-//            shuffles.  `ins` is the set of window positions inserted so far (probe positions,
-//            and ip-1 / ip after a copy -- insertion time is monotone in position).  A lane's
-//            precomputed result is exact unless an earlier lane of its hash group has been
-//            inserted in this window (grp & ins != 0); then the candidate is that lane and the
-//            match is re-measured (rare: a 4-byte repeat inside 32 bytes).
-//   commit: for every inserted lane that is the last inserted one of its group, table[h] = p
-//            -- the table the serial loop would have left.
-//
-// Literal runs use stride-1 probes only for their first 32 probes (encoder.nim:281-331: 16
-// unrolled + skip 48..63, or skip 32..63 near the end); longer runs (incompressible data) fall
-// back to the strided 32-probe windows of v1.
+// --------------------------------------------------------------------- input view and emit helpers of the window encoders
 struct InView {
   const uint32_t* w;  // 4-byte aligned base (global memory)
   uint32_t mis;       // byte offset of position 0 inside w[0]
@@ -413,13 +226,6 @@ __device__ __forceinline__ uint32_t in_ld4(const InView& v, uint32_t p) {
   uint32_t i = p + v.mis, k = i >> 2;
   uint32_t lo = __ldg(v.w + k), hi = __ldg(v.w + umin32(k + 1, v.last));
   return __funnelshift_r(lo, hi, (i & 3) * 8);
-}
-// 8 bytes at p; requires p + 8 <= len.
-__device__ __forceinline__ void in_ld8(const InView& v, uint32_t p, uint32_t& lo, uint32_t& hi) {
-  uint32_t i = p + v.mis, k = i >> 2, s = (i & 3) * 8;
-  uint32_t w0 = __ldg(v.w + k), w1 = __ldg(v.w + k + 1), w2 = __ldg(v.w + umin32(k + 2, v.last));
-  lo = __funnelshift_r(w0, w1, s);
-  hi = __funnelshift_r(w1, w2, s);
 }
 __device__ __forceinline__ uint32_t in_byte(const InView& v, uint32_t p) {
   return __ldg((const uint8_t*)v.w + v.mis + p);
@@ -448,24 +254,6 @@ __device__ __forceinline__ uint32_t common_prefix_v2(const InView& v, uint32_t l
     matched += 128; s1 += 128; s2 += 128;
   }
 }
-// Extension of a match known to be equal up to s1/s2: two uniform 8-byte steps (most matches
-// end within them), then the 128-byte-per-step warp compare.
-__device__ __forceinline__ uint32_t extend_match_v2(const InView& v, uint32_t len, uint32_t s1, uint32_t s2,
-                                                    uint32_t lane) {
-  uint32_t m = 0;
-#pragma unroll 1
-  for (int it = 0; it < 2 && s2 + m + 8 <= len; it++) {
-    uint32_t a_lo, a_hi, b_lo, b_hi;
-    in_ld8(v, s1 + m, a_lo, a_hi);
-    in_ld8(v, s2 + m, b_lo, b_hi);
-    uint32_t x_lo = a_lo ^ b_lo, x_hi = a_hi ^ b_hi;
-    if (x_lo) return m + ((uint32_t)(__ffs((int)x_lo) - 1) >> 3);
-    if (x_hi) return m + 4 + ((uint32_t)(__ffs((int)x_hi) - 1) >> 3);
-    m += 8;
-  }
-  return m + common_prefix_v2(v, len, s1 + m, s2 + m, lane);
-}
-
 __device__ __forceinline__ uint32_t emit_literal_v2(uint8_t* o, const InView& v, uint32_t s, uint32_t n, uint32_t lane) {
   uint32_t m = (n - 1) & 0xffff, w;
   if (m < 60) { w = 1; if (lane == 0) o[0] = (uint8_t)(m << 2); }
@@ -491,629 +279,12 @@ __device__ __forceinline__ uint32_t emit_copy_v2(uint8_t* o, uint32_t off, uint3
   return emit_copy_warp(o, off, len, lane);
 }
 
-__device__ __forceinline__ uint32_t compress_block_v2(const uint8_t* __restrict__ in, uint32_t len,
-                                                      uint8_t* __restrict__ out, uint16_t* table,
-                                                      uint32_t abort_thr, uint32_t lane) {
-  InView v;
-  v.mis = (uint32_t)((uintptr_t)in & 3);
-  v.w = (const uint32_t*)(in - v.mis);
-  v.last = (len + v.mis - 1) >> 2;
-  if (len < kMinNonLiteral) return emit_literal_v2(out, v, 0, len, lane);
-
-  uint32_t tsize = 256;
-  while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
-  const uint32_t mask = tsize - 1;
-  {
-    uint32_t* t32 = (uint32_t*)table;
-    for (uint32_t i = lane; i < tsize / 2; i += 32) t32[i] = 0;
-  }
-  const uint32_t ip_limit = len - kInputMargin;
-  const uint32_t below = (1u << lane) - 1u;  // lanes before mine
-  uint32_t op = 0;
-  uint32_t ip = 0;          // chain mode: position of the pending post-copy lookup
-  uint32_t next_emit = 0;   // literal mode: start of the pending literal
-  uint32_t pp = 1;          // literal mode: next probe position
-  uint32_t k = 0;           // literal mode: probes already done in this run
-  bool chain = false;
-
-// finishing sequence shared by every exit: emit in[from..len) and return (encoder.nim:249-253)
-#define SNB_FINISH(from)                                                          \
-  do {                                                                            \
-    uint32_t f_ = (from);                                                         \
-    if (f_ < len) {                                                               \
-      uint32_t n_ = len - f_;                                                     \
-      if (op + literal_size(n_) > abort_thr) return kAborted;                     \
-      op += emit_literal_v2(out + op, v, f_, n_, lane);                           \
-    }                                                                             \
-    return op;                                                                    \
-  } while (0)
-// deferred write of this window's simple copy tags (each lane wrote down its offset in myoff)
-#define SNB_FLUSH_TAGS()                                                          \
-  do {                                                                            \
-    if ((copymask >> lane) & 1u) {                                                \
-      uint8_t* o_ = out + myoff;                                                  \
-      o_[0] = (uint8_t)tagw; o_[1] = (uint8_t)(tagw >> 8);                        \
-      if (tagw >> 24) o_[2] = (uint8_t)(tagw >> 16);                              \
-    }                                                                             \
-  } while (0)
-
-  for (;;) {
-    __syncwarp();  // table writes (zeroing / previous commit) visible to every lane
-
-    if (!chain && k >= 32) {
-      // ---- long literal run: strided probes, 32 per step (encoder.nim:311-331 with skip >= 64)
-      uint32_t wip = pp, wskip = 32 + k;
-      uint32_t hit_ip = 0, hit_cand = 0;
-      bool found = false;
-      for (;;) {
-        uint32_t pos = wip, sk = wskip;
-        for (uint32_t j = 0; j < lane; j++) { uint32_t st = sk >> 5; sk += st; pos += st; }
-        uint32_t step = sk >> 5, sk_after = sk + step;
-        bool valid = (pos <= ip_limit) && (pos + step <= ip_limit);
-        uint32_t d = 0, h = 0x10000u + lane, tv = 0;
-        if (valid) { d = in_ld4(v, pos); h = hash14(d, mask); tv = table[h]; }
-        uint32_t grp = __match_any_sync(kFull, h);
-        uint32_t earlier = grp & below;
-        int src = earlier ? 31 - __clz((int)earlier) : (int)lane;
-        uint32_t pe = __shfl_sync(kFull, pos, src);
-        uint32_t c = earlier ? pe : tv;
-        bool hit = valid && (in_ld4(v, c) == d);
-        uint32_t hitmask = __ballot_sync(kFull, hit);
-        uint32_t vmask = __ballot_sync(kFull, valid);
-        if (hitmask) {
-          int kh = __ffs((int)hitmask) - 1;
-          uint32_t commit = (2u << kh) - 1u;
-          if (((commit >> lane) & 1u) && ((grp & commit) >> lane) == 1u) table[h] = (uint16_t)pos;
-          hit_ip = __shfl_sync(kFull, pos, kh);
-          hit_cand = __shfl_sync(kFull, c, kh);
-          found = true;
-          break;
-        }
-        if (vmask != kFull) break;
-        if ((grp >> lane) == 1u) table[h] = (uint16_t)pos;
-        wip = __shfl_sync(kFull, pos + step, 31);
-        wskip = __shfl_sync(kFull, sk_after, 31);
-        __syncwarp();
-      }
-      if (!found) SNB_FINISH(next_emit);
-      {
-        uint32_t n = hit_ip - next_emit;
-        if (op + literal_size(n) > abort_thr) return kAborted;
-        op += emit_literal_v2(out + op, v, next_emit, n, lane);
-      }
-      uint32_t m = 4 + common_prefix_v2(v, len, hit_cand + 4, hit_ip + 4, lane);
-      op += emit_copy_v2(out + op, hit_ip - hit_cand, m, lane);
-      ip = hit_ip + m;
-      if (op > abort_thr) return kAborted;
-      if (ip > ip_limit) SNB_FINISH(ip);
-      chain = true;
-      continue;
-    }
-
-    // ---- phase A: per-lane lookup against the table as of the window start
-    const uint32_t b = chain ? ip - 1 : pp;
-    const uint32_t p = b + lane;
-    uint32_t h = 0x10000u + lane, rec = 0, tagw = 0;
-    if (p <= ip_limit) {
-      uint32_t a_lo, a_hi, c_lo, c_hi;
-      in_ld8(v, p, a_lo, a_hi);
-      h = hash14(a_lo, mask);
-      uint32_t T = table[h];
-      in_ld8(v, T, c_lo, c_hi);
-      uint32_t x_lo = a_lo ^ c_lo, x_hi = a_hi ^ c_hi;
-      uint32_t ml = x_lo ? ((uint32_t)(__ffs((int)x_lo) - 1) >> 3) : (x_hi ? 4 + ((uint32_t)(__ffs((int)x_hi) - 1) >> 3) : 8);
-      // the copy tag a 4..7-byte match at this position would emit (encoder.nim:113-125)
-      uint32_t off = p - T;
-      bool c2 = off >= 2048;
-      uint32_t t0 = c2 ? (((ml - 1) << 2) | 2) : (((off >> 8) << 5) | ((ml - 4) << 2) | 1);
-      tagw = (t0 & 0xff) | ((off & 0xff) << 8) | (c2 ? (((off >> 8) & 0xff) << 16) | (1u << 24) : 0u);
-      rec = T | (ml << 16) | ((c2 ? 3u : 2u) << 24);
-    }
-    const uint32_t grp = __match_any_sync(kFull, h);
-    const uint32_t eg = grp & below;                             // earlier lanes of my hash group
-    const uint32_t hitbits = __ballot_sync(kFull, ((rec >> 16) & 0xff) >= 4);
-    const uint32_t lim_lane = ip_limit > b ? ip_limit - b : 0;   // probes need p + 1 <= ip_limit (:318-321)
-    uint32_t ins = 0, copymask = 0, myoff = 0;
-
-    // ---- phase B: walk the parse through the window
-    for (;;) {
-      uint32_t cand, m;
-      if (chain) {
-        const uint32_t l = ip - b;
-        if (l >= 32) break;
-        const uint32_t bl1 = 1u << (l - 1);
-        const uint32_t g = __shfl_sync(kFull, grp, (int)l);
-        const uint32_t q = __shfl_sync(kFull, rec, (int)l);
-        const uint32_t st = g & (ins | bl1);                    // same-hash positions inserted in this window
-        ins |= bl1 | (bl1 << 1);                                // encoder.nim:371-377: insert ip-1, look up + insert ip
-        m = (q >> 16) & 0xff;
-        if (st == 0 && m < 8) {
-          if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }   // :379-380
-          if (lane == l) myoff = op;                            // simple copy: tag written at window end
-          copymask |= bl1 << 1;
-          op += q >> 24;
-          ip += m;
-          if (ip > ip_limit) { SNB_FLUSH_TAGS(); if (op > abort_thr) return kAborted; SNB_FINISH(ip); }
-          continue;
-        }
-        if (st) {
-          cand = b + (uint32_t)(31 - __clz((int)st));
-          m = common_prefix_v2(v, len, cand, ip, lane);
-          if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }
-        } else {
-          cand = q & 0xffff;
-          m = 8 + extend_match_v2(v, len, cand + 8, ip + 8, lane);
-        }
-      } else {
-        const uint32_t l0 = pp - b;
-        if (l0 >= 32) break;
-        const uint32_t from_l0 = 0xffffffffu << l0;
-        // probe lanes of this run inside the window: stride 1 until k reaches 32, and p + 1 <= ip_limit
-        const uint32_t hi = umax32(l0, umin32(umin32(32u, l0 + (32 - k)), lim_lane));
-        const uint32_t range = from_l0 & (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u));
-        const uint32_t sm = __ballot_sync(kFull, (eg & (ins | from_l0)) != 0);   // stale: same hash inserted before me
-        const uint32_t ev = (hitbits | sm) & range;
-        const uint32_t end_lane = hi;
-        const uint32_t e = ev ? (uint32_t)(__ffs((int)ev) - 1) : 32u;
-        if (e >= end_lane) {                                     // every probe up to end_lane missed
-          if (end_lane > l0) ins |= (end_lane >= 32 ? 0xffffffffu : ((1u << end_lane) - 1u)) & from_l0;
-          k += end_lane - l0;
-          pp = b + end_lane;
-          if (end_lane < 32 && k < 32) { SNB_FLUSH_TAGS(); if (op > abort_thr) return kAborted; SNB_FINISH(next_emit); }
-          break;                                                 // window exhausted, or k == 32
-        }
-        if (e > l0) ins |= ((1u << e) - 1u) & from_l0;           // probes before e inserted, no hit
-        const uint32_t g = __shfl_sync(kFull, grp, (int)e);
-        const uint32_t q = __shfl_sync(kFull, rec, (int)e);
-        const uint32_t st = g & ins;
-        ins |= 1u << e;                                          // :293-294 insert before comparing
-        m = (q >> 16) & 0xff;
-        cand = q & 0xffff;
-        if (st) {
-          cand = b + (uint32_t)(31 - __clz((int)st));
-          m = common_prefix_v2(v, len, cand, b + e, lane);
-          if (m < 4) { k += e + 1 - l0; pp = b + e + 1; continue; }
-        }
-        ip = b + e;
-        const uint32_t n = ip - next_emit;                       // :336-338
-        if (op + literal_size(n) > abort_thr) return kAborted;
-        op += emit_literal_v2(out + op, v, next_emit, n, lane);
-        chain = true;
-        if (st == 0 && m < 8) {                                  // simple copy at lane e
-          if (lane == e) myoff = op;
-          copymask |= 1u << e;
-          op += q >> 24;
-          ip += m;
-          if (ip > ip_limit) { SNB_FLUSH_TAGS(); if (op > abort_thr) return kAborted; SNB_FINISH(ip); }
-          continue;
-        }
-        if (st == 0) m = 8 + extend_match_v2(v, len, cand + 8, ip + 8, lane);
-      }
-      // ---- general copy at ip against cand (:356-363): long, re-measured or many-tag copies
-      op += emit_copy_v2(out + op, ip - cand, m, lane);
-      ip += m;
-      if (ip > ip_limit) { SNB_FLUSH_TAGS(); if (op > abort_thr) return kAborted; SNB_FINISH(ip); }
-    }
-
-    // ---- window end: write the deferred copy tags, commit the inserts (last inserted lane of
-    // each hash group wins), bound the output
-    SNB_FLUSH_TAGS();
-    if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[h] = (uint16_t)p;
-    if (op > abort_thr) return kAborted;
-  }
-#undef SNB_FLUSH_TAGS
-#undef SNB_FINISH
-}
-
-// --------------------------------------------------------------------- encodeBlock, v3
-// Window-parallel parse.  Same byte-exact result as v1/v2, but the walk through a 32-position
-// window is itself data parallel:
-//
-//   fetch    lane l owns position b+l (b a multiple of 32): 12 own bytes, hash, table entry T,
-//            12 candidate bytes.  Issued one window ahead; T is re-read after the previous
-//            window's commit and the candidate reloaded only if the entry changed.
-//   resolve  match length ml (0..12) against T, copy tag, match.any group of the hash.
-//   parse    as a *chain arrival* (post-copy lookup, encoder.nim:364-380) every lane knows its
-//            event: the copy at itself (hit) or the literal up to the first hit lane after it,
-//            then the copy there; and so the next chain arrival J.  Pointer doubling over J
-//            (3 rounds: arrivals are >= 4 apart) marks the arrivals actually on the path and sums
-//            their output sizes, which gives every node its output offset.
-//   verify   the inserts implied by the path are exact unless a looked-up lane has an earlier lane
-//            of its hash group inserted in this window (its true candidate is then that lane), or
-//            a match reaches the 12-byte horizon.  The path is accepted up to the first such node;
-//            that node is redone by a serial step straight on the table (v1 style).
-//   commit   last inserted lane of each hash group writes the table.
-//
-// Chunk tails, strided literal runs (>= 32 probes) and the rare conflicts take the serial step.
-struct WinData {
-  uint32_t a0, a1, a2;  // in[p .. p+12)
-  uint32_t h, T;        // hash of a0, table entry as of the fetch
-  uint32_t c0, c1, c2;  // in[T .. T+12)
-};
 // 12 bytes at p, p + 12 <= len (no clamping needed: every touched word holds an input byte)
 __device__ __forceinline__ void in_ld12u(const InView& v, uint32_t p, uint32_t& b0, uint32_t& b1, uint32_t& b2) {
   uint32_t i = p + v.mis, k = i >> 2, s = (i & 3) * 8;
   uint32_t w0 = __ldg(v.w + k), w1 = __ldg(v.w + k + 1), w2 = __ldg(v.w + k + 2), w3 = __ldg(v.w + umin32(k + 3, v.last));
   b0 = __funnelshift_r(w0, w1, s); b1 = __funnelshift_r(w1, w2, s); b2 = __funnelshift_r(w2, w3, s);
 }
-// The four aligned words holding in[p .. p+12), left unshifted so that issuing the loads does not wait for them.
-struct Raw4 { uint32_t w0, w1, w2, w3; };
-__device__ __forceinline__ void in_ld_raw(const InView& v, uint32_t p, Raw4& r) {
-  uint32_t k = (p + v.mis) >> 2;
-  r.w0 = __ldg(v.w + k); r.w1 = __ldg(v.w + k + 1); r.w2 = __ldg(v.w + k + 2); r.w3 = __ldg(v.w + umin32(k + 3, v.last));
-}
-__device__ __forceinline__ void raw_to12(const InView& v, uint32_t p, const Raw4& r, uint32_t& b0, uint32_t& b1, uint32_t& b2) {
-  uint32_t s = ((p + v.mis) & 3) * 8;
-  b0 = __funnelshift_r(r.w0, r.w1, s); b1 = __funnelshift_r(r.w1, r.w2, s); b2 = __funnelshift_r(r.w2, r.w3, s);
-}
-__device__ __forceinline__ void win_load_a(const InView& v, uint32_t p, WinData& w) { in_ld12u(v, p, w.a0, w.a1, w.a2); }
-__device__ __forceinline__ void win_load_t(const uint16_t* table, uint32_t mask, WinData& w) {
-  w.h = hash14(w.a0, mask);
-  w.T = table[w.h];
-}
-__device__ __forceinline__ void win_load_c(const InView& v, WinData& w) { in_ld12u(v, w.T, w.c0, w.c1, w.c2); }
-
-constexpr uint32_t kStageWords = 352;   // per-warp staging in shared memory: own[2][16] + tab[2][32] + cand[2][4][32]
-__device__ __forceinline__ uint32_t compress_block_v3(const uint8_t* __restrict__ in, uint32_t len,
-                                                      uint8_t* __restrict__ out, uint16_t* table,
-                                                      uint32_t abort_thr, uint32_t lane, uint32_t stage_idx, bool tglobal) {
-  SNB_DYN_SMEM(smem_raw);
-  uint32_t* const stage = (uint32_t*)smem_raw + stage_idx;   // 32-bit index arithmetic on the shared window
-  InView v;
-  v.mis = (uint32_t)((uintptr_t)in & 3);
-  v.w = (const uint32_t*)(in - v.mis);
-  v.last = (len + v.mis - 1) >> 2;
-  if (len < kMinNonLiteral) return emit_literal_v2(out, v, 0, len, lane);
-
-  uint32_t tsize = 256;
-  while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
-  const uint32_t mask = tsize - 1;
-  {
-    uint32_t* t32 = (uint32_t*)table;
-    for (uint32_t i = lane; i < tsize / 2; i += 32) t32[i] = 0;
-  }
-  const uint32_t ip_limit = len - kInputMargin;
-  const uint32_t below = (1u << lane) - 1u;          // lanes before mine
-  const uint32_t above = ~((2u << lane) - 1u);       // lanes after mine
-  uint32_t op = 0;
-  uint32_t ip = 0;          // chain mode: position of the pending post-copy lookup (<= ip_limit)
-  uint32_t next_emit = 0;   // literal mode: start of the pending literal
-  uint32_t pp = 1;          // literal mode: next probe position
-  uint32_t k = 0;           // literal mode: probes already done in this run
-  bool chain = false, force_slow = false;
-  bool m1_done = false;     // chain mode, ip on a window boundary: ip-1 has already been inserted
-  constexpr uint32_t kNoWindow = 0xffffffffu;
-  WinData cur, n1, n2;       // n1 / n2 only carry (a, h, T)
-  // staging (shared memory, filled by cp.async one pass before it is read; slot = window index & 1)
-  uint32_t* const st_own = stage;          // [2][16]: the 12 aligned words holding a window's 44 bytes
-  uint32_t* const st_tab = stage + 32;     // [2][32]: the aligned word holding each lane's table entry
-  uint32_t* const st_cand = stage + 96;    // [2][4][32]: four aligned words at each lane's candidate
-  const uint32_t own_q = (lane + v.mis) >> 2, own_s = ((lane + v.mis) & 3) * 8;
-  uint32_t cur_b = kNoWindow, n1_b = kNoWindow, n2_b = kNoWindow, n3_b = kNoWindow;
-
-#define SNB_FINISH(from)                                                          \
-  do {                                                                            \
-    uint32_t f_ = (from);                                                         \
-    if (f_ < len) {                                                               \
-      uint32_t n_ = len - f_;                                                     \
-      if (op + literal_size(n_) > abort_thr) return kAborted;                     \
-      op += emit_literal_v2(out + op, v, f_, n_, lane);                           \
-    }                                                                             \
-    return op;                                                                    \
-  } while (0)
-
-  for (;;) {
-    __syncwarp();  // table writes (zeroing / previous commit / serial step) visible to every lane
-    const uint32_t b = (chain ? ip : pp) & ~31u;
-
-    if (force_slow || b + 32 >= ip_limit || (!chain && k >= 32)) {
-      SNB_STAT(force_slow ? 1 : ((b + 32 >= ip_limit) ? 2 : 3));
-      force_slow = false;
-      m1_done = false;
-      if (chain) {
-        SNB_STAT(4);
-        // ---- one serial chain step straight on the table (encoder.nim:364-380)
-        const uint32_t d1 = in_ld4(v, ip - 1), d = in_ld4(v, ip);
-        const uint32_t h1 = hash14(d1, mask), hh = hash14(d, mask);
-        const uint32_t tv = table[hh];
-        const uint32_t cand = (hh == h1) ? ip - 1 : tv;
-        __syncwarp();  // every lane has read before lane 0 writes
-        if (lane == 0) { table[h1] = (uint16_t)(ip - 1); table[hh] = (uint16_t)ip; }
-        const uint32_t m = common_prefix_v2(v, len, cand, ip, lane);
-        if (m < 4) { chain = false; next_emit = ip; pp = ip + 1; k = 0; continue; }   // :379-380
-        op += emit_copy_v2(out + op, ip - cand, m, lane);
-        ip += m;
-        if (op > abort_thr) return kAborted;
-        if (ip > ip_limit) SNB_FINISH(ip);
-        continue;
-      }
-      // ---- serial literal scan from (pp, k): 32 strided probes per step (encoder.nim:281-331)
-      SNB_STAT(5);
-      uint32_t wip = pp, wskip = 32 + k;
-      uint32_t hit_ip = 0, hit_cand = 0;
-      bool found = false;
-      for (;;) {
-        uint32_t pos = wip, sk = wskip;
-        for (uint32_t j = 0; j < lane; j++) { uint32_t st = sk >> 5; sk += st; pos += st; }
-        uint32_t step = sk >> 5, sk_after = sk + step;
-        bool valid = (pos <= ip_limit) && (pos + step <= ip_limit);
-        uint32_t d = 0, h = 0x10000u + lane, tv = 0;
-        if (valid) { d = in_ld4(v, pos); h = hash14(d, mask); tv = table[h]; }
-        uint32_t grp = __match_any_sync(kFull, h);
-        uint32_t earlier = grp & below;
-        int src = earlier ? 31 - __clz((int)earlier) : (int)lane;
-        uint32_t pe = __shfl_sync(kFull, pos, src);
-        uint32_t c = earlier ? pe : tv;
-        bool hit = valid && (in_ld4(v, c) == d);
-        uint32_t hitmask = __ballot_sync(kFull, hit);
-        uint32_t vmask = __ballot_sync(kFull, valid);
-        if (hitmask) {
-          int kh = __ffs((int)hitmask) - 1;
-          uint32_t commit = (2u << kh) - 1u;
-          if (((commit >> lane) & 1u) && ((grp & commit) >> lane) == 1u) table[h] = (uint16_t)pos;
-          hit_ip = __shfl_sync(kFull, pos, kh);
-          hit_cand = __shfl_sync(kFull, c, kh);
-          found = true;
-          break;
-        }
-        if (vmask != kFull) break;
-        if ((grp >> lane) == 1u) table[h] = (uint16_t)pos;
-        wip = __shfl_sync(kFull, pos + step, 31);
-        wskip = __shfl_sync(kFull, sk_after, 31);
-        __syncwarp();
-      }
-      if (!found) SNB_FINISH(next_emit);
-      {
-        uint32_t n = hit_ip - next_emit;
-        if (op + literal_size(n) > abort_thr) return kAborted;
-        op += emit_literal_v2(out + op, v, next_emit, n, lane);
-      }
-      uint32_t m = 4 + common_prefix_v2(v, len, hit_cand + 4, hit_ip + 4, lane);
-      op += emit_copy_v2(out + op, hit_ip - hit_cand, m, lane);
-      ip = hit_ip + m;
-      if (op > abort_thr) return kAborted;
-      if (ip > ip_limit) SNB_FINISH(ip);
-      chain = true;
-      continue;
-    }
-
-    // ---- window data for [b, b+32): every lane is a valid lookup position (b + 32 < ip_limit)
-    SNB_STAT(0);
-    const uint32_t p = b + lane;
-    if (chain && ip == b && !m1_done) {  // arrival on the window boundary after a serial step: ip-1 is not a lane here
-      const uint32_t d1 = in_ld4(v, ip - 1);
-      if (lane == 0) table[hash14(d1, mask)] = (uint16_t)(ip - 1);
-      __syncwarp();
-    }
-    m1_done = false;
-    // Software pipeline over windows, one stage per pass, staged through shared memory by cp.async:
-    //   own words (b+96) -> own bytes, hash, table word (b+64) -> table entry, candidate words (b+32).
-    // A pass first consumes what the previous pass staged, then issues its own copies.
-    const bool fresh = cur_b != b;
-    bool have1 = false, have2 = false, have3 = false;
-    const uint32_t wslot = (b >> 5) & 1u;
-    if (fresh) {
-      const bool seq = n1_b == b;
-      const bool seq2 = seq && n2_b == b + 32, seq3 = seq && n3_b == b + 64;
-      cp_async_wait_all();
-      __syncwarp();
-      if (seq) {
-        cur.a0 = n1.a0; cur.a1 = n1.a1; cur.a2 = n1.a2; cur.h = n1.h; cur.T = n1.T;
-        const uint32_t* sc = st_cand + wslot * 128 + lane;
-        const uint32_t cs = ((n1.T + v.mis) & 3) * 8;
-        const uint32_t w0 = sc[0], w1 = sc[32], w2 = sc[64], w3 = sc[96];
-        cur.c0 = __funnelshift_r(w0, w1, cs); cur.c1 = __funnelshift_r(w1, w2, cs); cur.c2 = __funnelshift_r(w2, w3, cs);
-      } else {
-        win_load_a(v, p, cur); win_load_t(table, mask, cur); win_load_c(v, cur);
-      }
-      cur_b = b;
-      have1 = b + 64 < ip_limit; have2 = b + 96 < ip_limit; have3 = b + 128 < ip_limit;
-      if (have1) {
-        if (seq2) {
-          n1.a0 = n2.a0; n1.a1 = n2.a1; n1.a2 = n2.a2; n1.h = n2.h;
-          n1.T = tglobal ? ((st_tab[(wslot ^ 1u) * 32 + lane] >> ((n2.h & 1u) * 16)) & 0xffffu) : n2.T;
-        } else {
-          win_load_a(v, p + 32, n1); win_load_t(table, mask, n1);
-        }
-      }
-      if (have2) {
-        if (seq3) {
-          const uint32_t* so = st_own + wslot * 16 + own_q;
-          const uint32_t w0 = so[0], w1 = so[1], w2 = so[2], w3 = so[3];
-          n2.a0 = __funnelshift_r(w0, w1, own_s); n2.a1 = __funnelshift_r(w1, w2, own_s); n2.a2 = __funnelshift_r(w2, w3, own_s);
-        } else {
-          win_load_a(v, p + 64, n2);
-        }
-        n2.h = hash14(n2.a0, mask);
-      }
-    }
-    const uint32_t Tnow = table[cur.h];   // re-validation against the committed table (consumed below)
-    if (fresh) {
-      if (have1) {
-        const uint32_t* src = v.w + ((n1.T + v.mis) >> 2);
-        uint32_t* sc = st_cand + (wslot ^ 1u) * 128 + lane;
-        cp_async4(sc, src); cp_async4(sc + 32, src + 1); cp_async4(sc + 64, src + 2); cp_async4(sc + 96, src + 3);
-        n1_b = b + 32;
-      } else n1_b = kNoWindow;
-      if (have2) {
-        if (tglobal) cp_async4(st_tab + wslot * 32 + lane, (const uint32_t*)table + (n2.h >> 1));
-        else n2.T = table[n2.h];
-        n2_b = b + 64;
-      } else n2_b = kNoWindow;
-      if (have3) {
-        if (lane < 12) cp_async4(st_own + (wslot ^ 1u) * 16 + lane, v.w + ((b + 96) >> 2) + lane);
-        n3_b = b + 96;
-      } else n3_b = kNoWindow;
-      cp_async_commit();
-    }
-#ifdef SNB_STATS
-    if (__ballot_sync(kFull, Tnow != cur.T)) SNB_STAT(10);
-#endif
-    if (Tnow != cur.T) { cur.T = Tnow; in_ld12u(v, Tnow, cur.c0, cur.c1, cur.c2); }
-
-    // ---- resolve
-    const uint32_t x0 = cur.a0 ^ cur.c0, x1 = cur.a1 ^ cur.c1, x2 = cur.a2 ^ cur.c2;
-    uint32_t ml;
-    {  // common prefix of the 12 own / candidate bytes: one find-first-set on the first differing word
-      const uint32_t xs = x0 ? x0 : (x1 ? x1 : x2);
-      const uint32_t base = x0 ? 0u : (x1 ? 4u : 8u);
-      ml = xs ? base + first_diff_byte(xs) : 12u;
-    }
-    const uint32_t off = p - cur.T;
-    const bool c2 = off >= 2048;   // ml <= 11 whenever the tag is used (encoder.nim:113-125)
-    const uint32_t tb = c2 ? ((((ml - 1) << 2) | 2u) | (off << 8))
-                           : ((((off >> 8) << 5) | ((ml - 4) << 2) | 1u) | ((off & 0xff) << 8));
-    const uint32_t rec = (tb & 0xffffffu) | (c2 ? 1u << 24 : 0u) | (ml << 25);
-    const uint32_t grp = __match_any_sync(kFull, cur.h);
-    const uint32_t eg = grp & below;                   // earlier lanes of my hash group
-    const bool hit = ml >= 4;
-    const uint32_t HB = __ballot_sync(kFull, hit);
-
-    uint32_t ins = 0;   // lanes inserted (accepted) in this pass
-    uint32_t c0;        // next chain-arrival lane (>= 32: outside the window)
-    bool done = false;  // block finished inside this pass (ip > ip_limit after a copy)
-    if (!chain) {
-      // ---- the literal run entering the window: stride-1 probes at lanes [l0, bend)
-      const uint32_t l0 = pp - b;
-      const uint32_t bend = umin32(32u, l0 + (32u - k));
-      const uint32_t range = (0xffffffffu << l0) & (bend >= 32 ? 0xffffffffu : ((1u << bend) - 1u));
-      const uint32_t qh = HB & range;
-      const uint32_t q0 = qh ? (uint32_t)__ffs((int)qh) - 1u : 32u;
-      const uint32_t run = range & (((2u << (q0 & 31)) - 1u) | (q0 >= 32 ? 0xffffffffu : 0u));   // probes performed
-      const uint32_t stale = __ballot_sync(kFull, (eg & run) != 0) & run;
-      if (stale) { SNB_STAT(6); force_slow = true; continue; }
-      if (q0 >= 32) {  // every probe missed: insert them and move on (k == 32 switches to the strided scan)
-        if (((run >> lane) & 1u) && ((grp & run) >> lane) == 1u) table[cur.h] = (uint16_t)p;
-        k += (uint32_t)__popc(run);
-        pp = b + bend;
-        continue;
-      }
-      const uint32_t q0rec = __shfl_sync(kFull, rec, (int)q0);
-      const uint32_t q0ml = q0rec >> 25;
-      {  // :336-338, then the copy at q0
-        const uint32_t n = b + q0 - next_emit;
-        if (op + literal_size(n) > abort_thr) return kAborted;
-        op += emit_literal_v2(out + op, v, next_emit, n, lane);
-      }
-      ins = run;
-      chain = true;
-      if (q0ml >= 12) {  // the match reaches the horizon: measure it (encoder.nim:130-182)
-        SNB_STAT(7);
-        const uint32_t cand = __shfl_sync(kFull, cur.T, (int)q0);
-        const uint32_t m = 12 + common_prefix_v2(v, len, cand + 12, b + q0 + 12, lane);
-        op += emit_copy_v2(out + op, b + q0 - cand, m, lane);
-        ip = b + q0 + m;
-      } else {
-        if (lane == 0) {
-          uint8_t* o = out + op;
-          o[0] = (uint8_t)q0rec; o[1] = (uint8_t)(q0rec >> 8);
-          if ((q0rec >> 24) & 1u) o[2] = (uint8_t)(q0rec >> 16);
-        }
-        op += ((q0rec >> 24) & 1u) ? 3u : 2u;
-        ip = b + q0 + q0ml;
-      }
-      if (ip > ip_limit) done = true;
-      c0 = ip - b;
-    } else {
-      c0 = ip - b;
-    }
-
-    if (c0 < 32 && !done) {
-      // ---- every lane as a chain arrival: its event lane, the next arrival, its output size
-      const uint32_t qb = hit ? (1u << lane) : (HB & above);
-      const uint32_t evt = qb ? (uint32_t)__ffs((int)qb) - 1u : 32u;
-      const uint32_t erec = __shfl_sync(kFull, rec, (int)(evt & 31));
-      const uint32_t eml = erec >> 25;
-      const uint32_t J0 = evt < 32 ? evt + eml : 64u;   // >= 32 leaves the window, 64: in literal mode
-      const uint32_t litn = evt - lane;
-      const uint32_t sz = evt < 32 ? (hit ? 0u : litn + 1u) + (((erec >> 24) & 1u) ? 3u : 2u) : 0u;
-      // inserts of a node: ip-1, ip, then the probes up to its event (encoder.nim:371-377, :293-294)
-      const uint32_t nmask = (0xffffffffu << (lane ? lane - 1 : 0)) & ((2u << (evt < 32 ? evt : 31u)) - 1u);
-      const bool elong = evt < 32 && eml >= 12;
-      for (;;) {
-        uint32_t J = J0, D = sz, R = 1u << c0;
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-          const uint32_t contrib = (((R >> lane) & 1u) && J < 32) ? (1u << J) : 0u;
-          R |= __reduce_or_sync(kFull, contrib);
-          const uint32_t jn = __shfl_sync(kFull, J, (int)(J & 31));
-          const uint32_t dn = __shfl_sync(kFull, D, (int)(J & 31));
-          if (J < 32) { D += dn; J = jn; }
-        }
-        const bool onp = (R >> lane) & 1u;
-        const uint32_t ins_all = ins | __reduce_or_sync(kFull, onp ? nmask : 0u);
-        const uint32_t stale = __ballot_sync(kFull, (eg & ins_all) != 0) & ins_all;
-        const bool mystale = (stale & nmask) != 0;
-        const uint32_t BAD = __ballot_sync(kFull, onp && (mystale || elong));
-        const uint32_t cb = BAD ? (uint32_t)__ffs((int)BAD) - 1u : 32u;
-        const uint32_t ACC = R & (cb >= 32 ? 0xffffffffu : ((1u << cb) - 1u));
-        const bool acc = (ACC >> lane) & 1u;
-        // what stops the accepted prefix: a stale lookup (serial step) or only the 12-byte horizon (measured here)
-        const bool cb_long = BAD && !__shfl_sync(kFull, (uint32_t)mystale, (int)(cb & 31));
-        const uint32_t take = cb_long ? (ACC | (1u << cb)) : ACC;    // nodes whose inserts are performed
-        ins = BAD ? (ins | __reduce_or_sync(kFull, ((take >> lane) & 1u) ? nmask : 0u)) : ins_all;
-        const uint32_t Dc0 = __shfl_sync(kFull, D, (int)c0);
-        const uint32_t Dcb = __shfl_sync(kFull, D, (int)(cb & 31));
-        const uint32_t off_me = op + (Dc0 - D);           // output offset of my node (accepted lanes)
-        if (acc && evt < 32) {
-          uint8_t* o = out + off_me;
-          if (!hit) { o[0] = (uint8_t)((litn - 1) << 2); o += 1 + litn; }
-          o[0] = (uint8_t)erec; o[1] = (uint8_t)(erec >> 8);
-          if ((erec >> 24) & 1u) o[2] = (uint8_t)(erec >> 16);
-        }
-        {  // literal bytes: lanes from a missed node up to its event write their own byte
-          const uint32_t nm = take & ((2u << lane) - 1u);
-          const uint32_t node = nm ? 31u - (uint32_t)__clz((int)nm) : 0u;
-          const uint32_t pk = __shfl_sync(kFull, off_me | (evt << 20) | (hit ? 1u << 26 : 0u), (int)node);
-          const uint32_t ev = (pk >> 20) & 63u;
-          if (nm && !((pk >> 26) & 1u) && ev < 32 && lane < ev) out[(pk & 0xfffffu) + 1 + (lane - node)] = (uint8_t)cur.a0;
-        }
-        op += Dc0 - (BAD ? Dcb : 0u);
-        if (!BAD) {
-          const uint32_t cl = 31u - (uint32_t)__clz((int)R);
-          const uint32_t Jl = __shfl_sync(kFull, J0, (int)cl);
-          if (Jl == 64u) { chain = false; next_emit = b + cl; pp = b + 32; k = 31 - cl; }
-          else ip = b + Jl;
-          break;
-        }
-        SNB_STAT(8);
-        if (!cb_long) { SNB_STAT(9); ip = b + cb; force_slow = true; break; }
-        // ---- node cb: (literal,) then a copy of at least 12 bytes, measured with the whole warp
-        const uint32_t pkb = __shfl_sync(kFull, evt | (hit ? 32u : 0u), (int)cb);
-        const uint32_t ev = pkb & 31u;
-        if (!(pkb & 32u)) {  // literal tag of the missed node (its bytes were written above)
-          if (lane == 0) out[op] = (uint8_t)((ev - cb - 1) << 2);
-          op += 1 + (ev - cb);
-        }
-        const uint32_t cand = __shfl_sync(kFull, cur.T, (int)ev);
-        const uint32_t m = 12 + common_prefix_v2(v, len, cand + 12, b + ev + 12, lane);
-        op += emit_copy_v2(out + op, b + ev - cand, m, lane);
-        ip = b + ev + m;
-        if (ip > ip_limit) { done = true; break; }
-        c0 = ip - b;
-        if (c0 >= 32) break;
-      }
-    }
-    if (chain && !force_slow && ip > ip_limit) done = true;   // encoder.nim:362-363
-    // the next arrival's ip-1 insert when no window pass will own it (lane c-1 of the node rule)
-    bool pend_insert = false;
-    if (chain && !force_slow && !done && (ip & 31u) == 0) {
-      if (ip == b + 32) ins |= 1u << 31; else pend_insert = true;
-      m1_done = true;
-    }
-    // ---- commit: the last inserted lane of each hash group writes the table
-    if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[cur.h] = (uint16_t)p;
-    if (op > abort_thr) return kAborted;
-    if (done) SNB_FINISH(ip);
-    if (pend_insert) {
-      __syncwarp();
-      const uint32_t d1 = in_ld4(v, ip - 1);
-      if (lane == 0) table[hash14(d1, mask)] = (uint16_t)(ip - 1);
-    }
-  }
-#undef SNB_FINISH
-}
-
 // --------------------------------------------------------------------- encodeBlock, v5
 // Window walk on ballot masks.  One pass handles the 32 positions [b, b+32) that hold the cursor:
 //
@@ -1438,7 +609,6 @@ struct CompressArgs {
   uint32_t count;
   uint32_t mode;
   uint32_t table_entries;   // per-warp shared-memory table capacity (u16 entries)
-  uint32_t algo;            // 1: compress_block_warp (v1), 2: compress_block_v2, otherwise compress_block_v3
   uint32_t defer_stored;    // 1: stored frames get only their header here (compact_kernel copies the payload)
   uint16_t* gtables;        // hash tables of the warps beyond smem_warps (table_entries each)
   uint32_t smem_warps;      // warps per CTA whose table lives in shared memory
@@ -1454,22 +624,10 @@ __device__ __forceinline__ uint32_t varint32_len(uint32_t v) {
   return v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5;
 }
 
-template <int kAlgo>
-__device__ __forceinline__ uint32_t encode_block(uint32_t algo, const uint8_t* in, uint32_t len, uint8_t* out,
-                                                 uint16_t* table, uint32_t abort_thr, uint32_t lane, uint32_t stage,
-                                                 bool tglobal) {
-  if (kAlgo == 5) return compress_block_v5(in, len, out, table, abort_thr, lane);
-  if (algo == 1) return compress_block_warp(in, len, out, table, abort_thr, lane);
-  if (algo == 2) return compress_block_v2(in, len, out, table, abort_thr, lane);
-  if (algo == 5) return compress_block_v5(in, len, out, table, abort_thr, lane);
-  return compress_block_v3(in, len, out, table, abort_thr, lane, stage, tglobal);
-}
-
 // One job = one encodeFrame (encoder.nim:385-426), one bare encodeBlock, or one whole
 // single-block `compress` message (snappy.nim:27-64).
-template <int kAlgo>
 __device__ __forceinline__ uint32_t compress_job(const CompressArgs& a, uint32_t job, uint16_t* table, uint32_t lane,
-                                                 uint32_t stage, bool tglobal, uint32_t crc_in = 0, bool publish = true) {
+                                                 uint32_t crc_in = 0, bool publish = true) {
   uint64_t ioff = a.in_off ? a.in_off[job] : (uint64_t)job * kMaxBlock;
   uint32_t len = a.in_len ? a.in_len[job] : (uint32_t)((a.total_len - ioff) < kMaxBlock ? (a.total_len - ioff) : kMaxBlock);
   uint64_t ooff = a.out_off ? a.out_off[job] : (uint64_t)job * a.out_stride;
@@ -1481,7 +639,7 @@ __device__ __forceinline__ uint32_t compress_job(const CompressArgs& a, uint32_t
   const uint32_t pre = frame ? 8u + hl : hl;
   const uint32_t thr = frame ? len - len / 8 : kNoAbort;
   uint32_t bl = frame ? kAborted : 0u;
-  if (frame ? len >= kMinNonLiteral : len > 0) bl = encode_block<kAlgo>(a.algo, in, len, out + pre, table, thr, lane, stage, tglobal);  // encoder.nim:401-406
+  if (frame ? len >= kMinNonLiteral : len > 0) bl = compress_block_v5(in, len, out + pre, table, thr, lane);  // encoder.nim:401-406
   uint32_t total;
   if (frame) {
     uint32_t crc = a.crc ? a.crc[job] : crc_in;
@@ -1510,32 +668,7 @@ __device__ __forceinline__ uint32_t compress_job(const CompressArgs& a, uint32_t
 
 // Persistent kernel: blockDim.x/32 warps per CTA pulling jobs from a global counter.  The first
 // `smem_warps` warps keep their hash table in dynamic shared memory; the others use a 32 KiB
-// slice of `gtables` (global memory, L2 resident: 148 x a few x 32 KiB) -- same code, the table
-// pointer is generic.  The extra warps are what fills the issue slots: one encoder warp is a
-// single dependent chain.
-#ifndef SNB_COMPRESS_MAXT
-#define SNB_COMPRESS_MAXT 640
-#endif
-constexpr uint32_t kCompressMaxThreads = SNB_COMPRESS_MAXT;  // register budget: 65536 / 640 = 102 per thread (no spills: spilled prefetch registers stall on their loads)
-__global__ void __launch_bounds__(kCompressMaxThreads, 1) compress_kernel(CompressArgs a) {
-  SNB_DYN_SMEM(smem);
-  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool tglobal = warp >= a.smem_warps;
-  uint16_t* table = !tglobal
-                        ? (uint16_t*)smem + (size_t)warp * a.table_entries
-                        : a.gtables + ((size_t)blockIdx.x * (blockDim.x / 32 - a.smem_warps) + (warp - a.smem_warps)) * a.table_entries;
-  // per-warp staging area of the v3 encoder, behind the shared-memory tables
-  const uint32_t stage = a.smem_warps * a.table_entries / 2 + warp * kStageWords;   // word index into the dynamic shared memory
-  for (;;) {
-    uint32_t job = 0;
-    if (lane == 0) job = atomicAdd(a.counter, 1u);
-    job = __shfl_sync(kFull, job, 0);
-    if (job >= a.count) return;
-    compress_job<0>(a, job, table, lane, stage, tglobal);
-    __syncwarp();
-  }
-}
-
+// slice of `gtables` (global memory, L2 resident) -- same code, the table pointer is generic.
 // The v5 encoder on its own register budget (no staging area: the tables are the only shared memory).
 #ifndef SNB_COMPRESS5_MAXT
 #define SNB_COMPRESS5_MAXT 704
@@ -1553,7 +686,7 @@ __global__ void __launch_bounds__(kCompress5MaxThreads, 1) compress_kernel5(Comp
     if (lane == 0) job = atomicAdd(a.counter, 1u);
     job = __shfl_sync(kFull, job, 0);
     if (job >= a.count) return;
-    compress_job<5>(a, job, table, lane, 0, tglobal);
+    compress_job(a, job, table, lane);
     __syncwarp();
   }
 }
@@ -1768,7 +901,7 @@ __global__ void __launch_bounds__(kStreamMaxThreads, 1) compress_stream_kernel(S
       crc = crc_mask(crc32c_warp(*crc_t, a.crc_tables, a.c.in_base + ioff, len, lane));
     }
 #endif
-    const uint32_t total = compress_job<5>(a.c, job, table, lane, 0, tglobal, crc, false);
+    const uint32_t total = compress_job(a.c, job, table, lane, crc, false);
 #if SNB_CRC_AFTER
     // The CRC pass reads the chunk AFTER the encoder has walked it: the bytes are still in L2 from the parse, and a
     // chunk that has only just been dequeued does not occupy 64 KiB of L2 before its first window is looked at.
@@ -1807,239 +940,6 @@ __global__ void stream_init_kernel(unsigned long long* frontier, const unsigned 
     *frontier = b << 24;
     *total = b;
   }
-}
-
-// --------------------------------------------------------------------- encodeBlock, one THREAD per block
-// For large batches the serial chain of the reference's loop (encoder.nim:184-383) is better
-// hidden by running every block at once: one thread per 64 KiB block, hash table in global
-// memory (32 KiB per thread, zeroed by the host).  The loop is restated as a LOCKSTEP state
-// machine so that the 32 blocks of a warp never serialise their memory latencies: every
-// iteration each lane performs exactly one of
-//   SCAN    one literal-scan probe            (encoder.nim:281-331)
-//   CHAIN   one post-copy insert + lookup     (encoder.nim:364-380)
-//   EXTEND  12 more bytes of findMatchLength  (encoder.nim:130-182)
-//   LIT     16 more bytes of a long literal   (encoder.nim:57-73)
-// with all parse-independent loads issued first, then the table access, then the candidate
-// bytes, then a divergent but memory-free state update.  Output goes through a per-thread
-// byte writer that only issues aligned 32-bit stores.
-enum : uint32_t { kTScan = 0, kTChain = 1, kTExtend = 2, kTLit = 3, kTDone = 4 };
-
-struct TWriter {
-  uint32_t* w;     // next aligned word of the output slot
-  uint32_t lo, hi; // pending bytes (low `fill` bytes of lo valid, hi = overflow of the last put)
-  uint32_t fill;   // 0..3 between puts
-};
-// append k (1..4) bytes held in the low bytes of v (no bits above 8k set)
-__device__ __forceinline__ void tw_put(TWriter& b, uint32_t v, uint32_t k) {
-  uint32_t sh = 8 * b.fill;
-  b.lo |= v << sh;
-  b.hi = __funnelshift_l(v, 0, sh);
-  b.fill += k;
-  if (b.fill >= 4) { *b.w++ = b.lo; b.lo = b.hi; b.fill -= 4; }
-}
-__device__ __forceinline__ void tw_flush(TWriter& b) {
-  uint8_t* p = (uint8_t*)b.w;
-  for (uint32_t i = 0; i < b.fill; i++) p[i] = (uint8_t)(b.lo >> (8 * i));
-}
-// k (0..16) bytes held in b0..b3
-__device__ __forceinline__ void tw_put16(TWriter& b, uint32_t k, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
-  const uint32_t w[4] = {b0, b1, b2, b3};
-#pragma unroll
-  for (uint32_t j = 0; j < 4; j++) {
-    if (k > 4 * j) {
-      uint32_t kk = umin32(4, k - 4 * j);
-      tw_put(b, kk == 4 ? w[j] : (w[j] & ((1u << (8 * kk)) - 1u)), kk);
-    }
-  }
-}
-// literal tag of an n-byte literal (encoder.nim:57-73); returns its size
-__device__ __forceinline__ uint32_t tw_literal_tag(TWriter& b, uint32_t n) {
-  uint32_t m = (n - 1) & 0xffff;
-  if (m < 60) { tw_put(b, m << 2, 1); return 1; }
-  if (m < 256) { tw_put(b, (60u << 2) | (m << 8), 2); return 2; }
-  tw_put(b, (61u << 2) | (m << 8), 3);
-  return 3;
-}
-// encoder.nim:81-125; returns bytes appended
-__device__ __forceinline__ uint32_t tw_copy(TWriter& b, uint32_t off, uint32_t len) {
-  uint32_t w = 0;
-  while (len >= 68) { tw_put(b, ((63u << 2) | 2u) | (off << 8), 3); w += 3; len -= 64; }
-  if (len > 64) { tw_put(b, ((59u << 2) | 2u) | (off << 8), 3); w += 3; len -= 60; }
-  if (len >= 12 || off >= 2048) { tw_put(b, (((len - 1) << 2) | 2u) | (off << 8), 3); return w + 3; }
-  tw_put(b, (((off >> 8) << 5) | ((len - 4) << 2) | 1u) | ((off & 0xff) << 8), 2);
-  return w + 2;
-}
-// n (12 / 16) bytes at position p as little-endian words; words past the input end repeat the last one
-__device__ __forceinline__ void in_ld12(const InView& v, uint32_t p, uint32_t& b0, uint32_t& b1, uint32_t& b2) {
-  uint32_t i = p + v.mis, k = i >> 2, s = (i & 3) * 8;
-  uint32_t w0 = __ldg(v.w + umin32(k, v.last)), w1 = __ldg(v.w + umin32(k + 1, v.last));
-  uint32_t w2 = __ldg(v.w + umin32(k + 2, v.last)), w3 = __ldg(v.w + umin32(k + 3, v.last));
-  b0 = __funnelshift_r(w0, w1, s); b1 = __funnelshift_r(w1, w2, s); b2 = __funnelshift_r(w2, w3, s);
-}
-__device__ __forceinline__ void in_ld16(const InView& v, uint32_t p, uint32_t& b0, uint32_t& b1, uint32_t& b2,
-                                        uint32_t& b3) {
-  uint32_t i = p + v.mis, k = i >> 2, s = (i & 3) * 8;
-  uint32_t w0 = __ldg(v.w + umin32(k, v.last)), w1 = __ldg(v.w + umin32(k + 1, v.last));
-  uint32_t w2 = __ldg(v.w + umin32(k + 2, v.last)), w3 = __ldg(v.w + umin32(k + 3, v.last));
-  uint32_t w4 = __ldg(v.w + umin32(k + 4, v.last));
-  b0 = __funnelshift_r(w0, w1, s); b1 = __funnelshift_r(w1, w2, s);
-  b2 = __funnelshift_r(w2, w3, s); b3 = __funnelshift_r(w3, w4, s);
-}
-
-// Returns the encoded length (bytes appended to `wr`), or kAborted once the output would pass abort_thr.
-__device__ __forceinline__ uint32_t compress_block_thread(const uint8_t* __restrict__ in, uint32_t len, TWriter& wr,
-                                                          uint16_t* __restrict__ table, uint32_t abort_thr) {
-  InView v;
-  v.mis = (uint32_t)((uintptr_t)in & 3);
-  v.w = (const uint32_t*)(in - v.mis);
-  v.last = (len + v.mis - 1) >> 2;
-  if (len < kMinNonLiteral) {  // encoder.nim:227-229
-    uint32_t b0, b1, b2, b3;
-    in_ld16(v, 0, b0, b1, b2, b3);
-    uint32_t t = tw_literal_tag(wr, len);
-    tw_put16(wr, len, b0, b1, b2, b3);
-    return t + len;
-  }
-  uint32_t tsize = 256;
-  while (tsize < kMaxTableEntries && tsize < len) tsize <<= 1;
-  const uint32_t mask = tsize - 1;
-  const uint32_t ip_limit = len - kInputMargin;
-
-  uint32_t mode = kTScan, op = 0;
-  uint32_t ip = 1, next_emit = 0, skip = 33, next_ip = 2;   // first probe of the first run (ip_limit >= 2)
-  uint32_t e_s1 = 0, e_s2 = 0, e_matched = 0, e_off = 0;    // EXTEND
-  uint32_t lit_src = 0, lit_n = 0;                          // LIT
-  uint32_t pend_cand = 0, pend_ml = 0;                      // LIT: the copy that follows (pend_ml == 0: block ends)
-  bool aborted = false;
-
-  // emitRemainder (encoder.nim:249-253 via :319-321 / :362-363)
-  auto finish_from = [&](uint32_t from) {
-    if (from >= len) { mode = kTDone; return; }
-    uint32_t n = len - from;
-    if (op + literal_size(n) > abort_thr) { aborted = true; mode = kTDone; return; }
-    op += tw_literal_tag(wr, n) + n;
-    lit_src = from; lit_n = n; pend_ml = 0; mode = kTLit;
-  };
-  // next probe of the current run: encoder.nim:311-321 (and the unrolled :281-309, same recurrence)
-  auto arm_scan = [&]() {
-    uint32_t step = skip >> 5;
-    skip += step;
-    next_ip = ip + step;
-    if (next_ip > ip_limit) finish_from(next_emit); else mode = kTScan;
-  };
-  // a copy of `matched` bytes at ip has been emitted (encoder.nim:358-363)
-  auto after_copy = [&](uint32_t matched) {
-    ip += matched;
-    if (op > abort_thr) { aborted = true; mode = kTDone; return; }
-    if (ip > ip_limit) finish_from(ip); else mode = kTChain;
-  };
-  // the match at ip against cand is known to be ml (4..8, 8 = at least 8) bytes long
-  auto begin_copy = [&](uint32_t cand, uint32_t ml) {
-    if (ml >= 8) {
-      e_s1 = cand + 8; e_s2 = ip + 8; e_matched = 8; e_off = ip - cand; mode = kTExtend;
-    } else {
-      op += tw_copy(wr, ip - cand, ml);
-      after_copy(ml);
-    }
-  };
-
-  while (mode != kTDone) {
-    const bool probing = mode <= kTChain;
-    const uint32_t pa = probing ? ip - 1 : e_s2;
-    const uint32_t pb = mode == kTScan ? next_emit : (mode == kTExtend ? e_s1 : lit_src);
-    uint32_t a0, a1, a2, b0, b1, b2, b3;
-    in_ld12(v, pa, a0, a1, a2);
-    in_ld16(v, pb, b0, b1, b2, b3);
-    if (probing) {
-      const uint32_t d = __funnelshift_r(a0, a1, 8), dhi = __funnelshift_r(a1, a2, 8);
-      if (mode == kTChain) table[hash14(a0, mask)] = (uint16_t)(ip - 1);   // :371
-      const uint32_t h = hash14(d, mask);
-      const uint32_t cand = table[h];                                      // :293 / :375
-      table[h] = (uint16_t)ip;                                             // :294 / :377
-      uint32_t c_lo, c_hi;
-      in_ld8(v, cand, c_lo, c_hi);
-      const uint32_t x_lo = d ^ c_lo, x_hi = dhi ^ c_hi;
-      const uint32_t ml = x_lo ? first_diff_byte(x_lo) : (x_hi ? 4 + first_diff_byte(x_hi) : 8);
-      if (ml >= 4) {
-        if (mode == kTScan) {                                              // :336-338
-          const uint32_t n = ip - next_emit;
-          if (op + literal_size(n) > abort_thr) { aborted = true; mode = kTDone; continue; }
-          op += tw_literal_tag(wr, n) + n;
-          if (n > 16) { lit_src = next_emit; lit_n = n; pend_cand = cand; pend_ml = ml; mode = kTLit; continue; }
-          tw_put16(wr, n, b0, b1, b2, b3);
-        }
-        begin_copy(cand, ml);
-      } else if (mode == kTScan) {
-        ip = next_ip;
-        arm_scan();
-      } else {                                                             // :379-380 -> :255-258
-        next_emit = ip; ip += 1; skip = 32;
-        arm_scan();
-      }
-    } else if (mode == kTExtend) {
-      const uint32_t rem = len - e_s2;
-      const uint32_t x0 = a0 ^ b0, x1 = a1 ^ b1, x2 = a2 ^ b2;
-      uint32_t k = x0 ? first_diff_byte(x0) : (x1 ? 4 + first_diff_byte(x1) : (x2 ? 8 + first_diff_byte(x2) : 12));
-      k = umin32(k, rem);
-      e_matched += k;
-      if (k == 12) { e_s1 += 12; e_s2 += 12; continue; }
-      op += tw_copy(wr, e_off, e_matched);
-      after_copy(e_matched);
-    } else {  // kTLit
-      const uint32_t k = umin32(16, lit_n);
-      tw_put16(wr, k, b0, b1, b2, b3);
-      lit_src += k; lit_n -= k;
-      if (lit_n == 0) {
-        if (pend_ml) begin_copy(pend_cand, pend_ml); else mode = kTDone;
-      }
-    }
-  }
-  return aborted ? kAborted : op;
-}
-
-struct CompressTArgs {
-  const uint8_t* in_base;   // contiguous stream, block i = bytes [65536 i, ...)
-  uint8_t* out_base;        // scratch slots (4-byte aligned, stride a multiple of 4)
-  uint16_t* tables;         // count x 16384 entries, zeroed
-  uint64_t total_len;
-  uint64_t out_stride;
-  const uint32_t* crc;
-  uint32_t* out_len;
-  uint32_t count;
-  uint32_t mode;            // kModeFrame or kModeRawBlock
-};
-// Frames: stored chunks only get their 8-byte header here; compact_kernel takes the payload
-// straight from the input (slot[0] == 0x01 marks them).
-__global__ void __launch_bounds__(32) compress_thread_kernel(CompressTArgs a) {
-  uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
-  if (job >= a.count) return;
-  uint64_t ioff = (uint64_t)job * kMaxBlock;
-  uint32_t len = (uint32_t)((a.total_len - ioff) < kMaxBlock ? (a.total_len - ioff) : kMaxBlock);
-  const uint8_t* in = a.in_base + ioff;
-  uint32_t* slot = (uint32_t*)(a.out_base + (uint64_t)job * a.out_stride);
-  uint16_t* table = a.tables + (size_t)job * kMaxTableEntries;
-  uint32_t total;
-  TWriter wr;
-  wr.hi = 0;
-  if (a.mode == kModeFrame) {  // encoder.nim:385-426
-    uint32_t hl = varint32_len(len), thr = len - len / 8, bl = kAborted, fl;
-    // the block starts right after the 8-byte frame header and the varint: seed the writer with the varint
-    uint32_t vb = 0;
-    { uint32_t x = len, i = 0; while (x >= 0x80) { vb |= ((x & 0x7f) | 0x80) << (8 * i++); x >>= 7; } vb |= x << (8 * i); }
-    wr.w = slot + 2; wr.lo = vb; wr.fill = hl;
-    if (len >= kMinNonLiteral) bl = compress_block_thread(in, len, wr, table, thr);
-    uint32_t type = 0x01;
-    if (bl != kAborted && bl <= thr) { fl = hl + bl + 4; type = 0x00; tw_flush(wr); }
-    else fl = len + 4;
-    slot[0] = type | (fl << 8);
-    slot[1] = a.crc[job];
-    total = fl + 4;
-  } else {
-    wr.w = slot; wr.lo = 0; wr.fill = 0;
-    total = compress_block_thread(in, len, wr, table, kNoAbort);
-    tw_flush(wr);
-  }
-  a.out_len[job] = total;
 }
 
 // ===================================================================== CRC kernels
@@ -2098,36 +998,6 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* lens, uint64
     __syncthreads();
   }
   if (threadIdx.x == 0) *total = carry_s;
-}
-
-// Cooperative CTA copy, any alignment: dst-aligned 32-bit stores, funnel-shifted loads.
-__device__ __forceinline__ void block_copy(uint8_t* d, const uint8_t* s, uint32_t n) {
-  uint32_t head = umin32(n, (uint32_t)((0 - (uintptr_t)d) & 3));
-  if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
-  uint32_t words = (n - head) >> 2;
-  uint32_t* dw = (uint32_t*)(d + head);
-  const uint8_t* sp = s + head;
-  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dw[i] = load32u(sp + 4 * i);
-  uint32_t done = head + 4 * words;
-  if (threadIdx.x < n - done) d[done + threadIdx.x] = s[done + threadIdx.x];
-}
-// Gather variable-length job outputs (slot i at i*stride, lens[i] bytes) to dst + offs[i].
-// One CTA per job (grid-stride).  With `in_base` set (framed mode), a stored chunk (slot[0] == 0x01)
-// only has its 8-byte header in the slot; its payload is block i of the input.
-__global__ void __launch_bounds__(256) compact_kernel(const uint8_t* scratch, uint64_t stride, const uint32_t* lens,
-                                                      const uint64_t* offs, uint8_t* dst, uint32_t count,
-                                                      const uint8_t* in_base) {
-  for (uint32_t job = blockIdx.x; job < count; job += gridDim.x) {
-    const uint8_t* s = scratch + (uint64_t)job * stride;
-    uint8_t* d = dst + offs[job];
-    uint32_t n = lens[job];
-    if (in_base != nullptr && s[0] == 0x01) {
-      if (threadIdx.x < 8) d[threadIdx.x] = s[threadIdx.x];
-      block_copy(d + 8, in_base + (uint64_t)job * kMaxBlock, n - 8);
-    } else {
-      block_copy(d, s, n);
-    }
-  }
 }
 
 // ===================================================================== decompress

@@ -7,8 +7,8 @@
 //
 //   scan      every stream position is tested for "could be a chunk header": a type the walk accepts (0x00, 0x01,
 //             >= 0x80) whose length fits the stream and, for data chunks, passes the reference's own size / varint
-//             checks (skippable chunks: up to 64 KiB).  Random payload bytes pass about once in 500 positions;
-//             candidates are kept in stream order.
+//             checks (skippable chunks: up to 64 KiB), and whose successor position passes the same test or is the
+//             end of the stream.  Candidates are kept in stream order.
 //   link      a candidate's successor is the candidate at position + 4 + length (binary search), the end of the
 //             stream, or nothing.
 //   reach     starting from the first header the reachable set doubles per round (pointer jumping): after
@@ -26,7 +26,7 @@ namespace fidx {
 
 constexpr uint32_t kScanThreads = 256;
 constexpr uint32_t kScanBytes = 32768;          // stream bytes per CTA
-constexpr uint32_t kBlockCands = 256;           // candidate slots per CTA (random payload: ~80 per 32 KiB)
+constexpr uint32_t kBlockCands = 512;           // candidate slots per CTA (after the successor check: a handful per 32 KiB)
 constexpr uint32_t kEnd = 0xfffffffeu, kDead = 0xffffffffu;
 constexpr uint32_t kMaxSkippable = 1u << 16;    // longest skippable chunk the candidate scan considers
 
@@ -94,6 +94,10 @@ __device__ __forceinline__ bool header_ok(const uint8_t* s, unsigned long long n
   return false;
 }
 
+__device__ __forceinline__ uint32_t load_hdr(const uint8_t* s, unsigned long long p) {
+  return ld_u8(s + p) | (ld_u8(s + p + 1) << 8) | (ld_u8(s + p + 2) << 16) | (ld_u8(s + p + 3) << 24);
+}
+
 // scan: candidates of each 32 KiB piece of the stream, in stream order, into the CTA's slots.
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(Args a) {
   __shared__ unsigned long long list[kBlockCands];
@@ -125,6 +129,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(Args a) {
       if (id >= 0x80u && (hdr >> 8) > kMaxSkippable) continue;
       uint32_t kind, ul;
       if (!header_ok(s, a.n, p, hdr, &kind, &ul)) continue;
+      // ... and so must its successor be (or the stream ends there).  Payload bytes that look like a header (JPEG data is
+      // full of ff 00 xx yy) almost never point at another plausible header.  A TRUE header in front of a malformed one
+      // is dropped by this too: the chain then stops short of the end, and the host walk reports the exact error.
+      const unsigned long long t = p + 4 + (hdr >> 8);
+      if (t != a.n) {
+        if (a.n - t < 4) continue;
+        uint32_t k2, u2;
+        if (!header_ok(s, a.n, t, load_hdr(s, t), &k2, &u2)) continue;
+      }
       const uint32_t slot = atomicAdd(&cnt, 1u);
       if (slot < kBlockCands) list[slot] = p;
     }
@@ -156,10 +169,6 @@ __global__ void __launch_bounds__(256) gather_kernel(Args a) {
   const uint32_t c = a.blk_count[b];
   const unsigned long long o = a.blk_off[b];
   for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) a.cand[o + i] = a.cand_tmp[(unsigned long long)b * kBlockCands + i];
-}
-
-__device__ __forceinline__ uint32_t load_hdr(const uint8_t* s, unsigned long long p) {
-  return ld_u8(s + p) | (ld_u8(s + p + 1) << 8) | (ld_u8(s + p + 2) << 16) | (ld_u8(s + p + 3) << 24);
 }
 
 // link: successor of every candidate; mark the start node.

@@ -82,20 +82,24 @@ def test_decoder_differential_fuzz(emu_api, oracle):
         P.check_framed_decode_parity(emu_api, oracle, s, 4096)
 
 
-@pytest.mark.parametrize("algo", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("algo", [5, 6])
 def test_every_block_encoder_variant(emu_api, oracle, algo):
-    """The three block encoders (per-step warp, window-resolve warp, thread-per-block with the table in
-    global memory) are byte-identical; the auto mode picks between the last two by batch size."""
+    """The two selectable encoders for 64 KiB chunks (5: one warp per chunk, the default; 6: resolver warps + walker
+    warp with the record ring) are byte-identical to the oracle, including the chunks v6 hands to v5 (short last chunk)."""
     lib = emu_api.lib
     lib.snb_set_compress_algo(algo)
     try:
-        for name, cut in [("alice29.txt", 70000), ("paper-100k.pdf", 102400), ("kppkn.gtb", 20000)]:
+        for name, cut in [("alice29.txt", 140000), ("paper-100k.pdf", 102400), ("kppkn.gtb", 70000), ("html_x_4", 140000),
+                          ("fireworks.jpeg", 70000), ("urls.10K", 131072)]:
             d = read_data(name)[:cut]
             P.check_raw(emu_api, oracle, d)
             P.check_framed(emu_api, oracle, d)
-        for n in [0, 1, 16, 17, 18, 300, 65535, 65536, 65537]:
+        for n in [0, 1, 16, 17, 18, 300, 65535, 65536, 65537, 131072]:
             P.check_framed(emu_api, oracle, bytes(i & 0xFF for i in range(n)))
             P.check_raw(emu_api, oracle, bytes(n))
+        rng = np.random.default_rng(31)
+        for alphabet in (2, 4, 64):                                 # dense short matches: many same-window hash groups
+            P.check_framed(emu_api, oracle, rng.integers(0, alphabet, 65536 + 777, dtype=np.uint8).tobytes())
     finally:
         lib.snb_set_compress_algo(0)
 
