@@ -397,6 +397,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
         if (hitmask) {
           int kh = __ffs((int)hitmask) - 1;
           uint32_t commit = (2u << kh) - 1u;
+          __syncwarp();   // every lane's table read of this step precedes the writes (WAR; the collectives above already imply it)
           if (((commit >> lane) & 1u) && ((grp & commit) >> lane) == 1u) table[h] = (uint16_t)pos;
           hit_ip = __shfl_sync(kFull, pos, kh);
           hit_cand = __shfl_sync(kFull, c, kh);
@@ -404,6 +405,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
           break;
         }
         if (vmask != kFull) break;
+        __syncwarp();
         if ((grp >> lane) == 1u) table[h] = (uint16_t)pos;
         wip = __shfl_sync(kFull, pos + step, 31);
         wskip = __shfl_sync(kFull, sk_after, 31);
@@ -492,6 +494,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       if (stale) { SNB_STAT(5); force_slow = true; continue; }
       if (q0 >= 32) {  // every probe missed: insert them and move on (k == 32 switches to the strided scan)
         SNB_STAT(6);
+        __syncwarp();
         if (((run >> lane) & 1u) && ((grp & run) >> lane) == 1u) table[h] = (uint16_t)p;
         k += (uint32_t)__popc(run);
         pp = b + bend;
@@ -584,6 +587,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     prefetch_l2(v.w + ((Tn + v.mis) >> 2));
 #endif
     // ---- commit: the last inserted lane of each hash group writes the table
+    __syncwarp();   // after every lane's reads of this pass (WAR: racecheck-clean; the ballots above already order them in practice)
     if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[h] = (uint16_t)p;
     if (done) SNB_FINISH(ip);
     if (pend_insert) {

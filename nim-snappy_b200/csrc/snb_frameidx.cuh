@@ -7,8 +7,8 @@
 //
 //   scan      every stream position is tested for "could be a chunk header": a type the walk accepts (0x00, 0x01,
 //             >= 0x80) whose length fits the stream and, for data chunks, passes the reference's own size / varint
-//             checks (skippable chunks: up to 64 KiB), and whose successor position passes the same test or is the
-//             end of the stream.  Candidates are kept in stream order.
+//             checks (skippable chunks: up to 64 KiB), and that leads to three more such headers or to the end of
+//             the stream.  Candidates are kept in stream order.
 //   link      a candidate's successor is the candidate at position + 4 + length (binary search), the end of the
 //             stream, or nothing.
 //   reach     starting from the first header the reachable set doubles per round (pointer jumping): after
@@ -24,9 +24,12 @@
 namespace snb {
 namespace fidx {
 
-constexpr uint32_t kScanThreads = 256;
+constexpr uint32_t kScanThreads = 1024;         // 8 words per thread and CTA: the scan is bound by DRAM latency, so many warps and a prefetch
 constexpr uint32_t kScanBytes = 32768;          // stream bytes per CTA
-constexpr uint32_t kBlockCands = 512;           // candidate slots per CTA (after the successor check: a handful per 32 KiB)
+constexpr uint32_t kBlockCands = 1024;          // candidate slots per CTA (after the successor checks: a handful per 32 KiB)
+constexpr uint32_t kStage1 = 8192;              // positions per CTA that pass the register-only test (text: ~200 of 32 768)
+constexpr uint32_t SNB_MAX_FRAME_DATA = 76490u + 4u;   // codec.nim:216-219 + the CRC
+constexpr uint32_t kHops = 3;                   // successors a candidate must lead to (or the end of the stream)
 constexpr uint32_t kEnd = 0xfffffffeu, kDead = 0xffffffffu;
 constexpr uint32_t kMaxSkippable = 1u << 16;    // longest skippable chunk the candidate scan considers
 
@@ -98,49 +101,75 @@ __device__ __forceinline__ uint32_t load_hdr(const uint8_t* s, unsigned long lon
   return ld_u8(s + p) | (ld_u8(s + p + 1) << 8) | (ld_u8(s + p + 2) << 16) | (ld_u8(s + p + 3) << 24);
 }
 
-// scan: candidates of each 32 KiB piece of the stream, in stream order, into the CTA's slots.
+// scan: candidates of each 32 KiB piece of the stream, in stream order, into the CTA's slots.  Two stages, because the
+// full test needs bytes from elsewhere in the stream: done inline, the few lanes that get that far stall their whole warp
+// on dependent loads in almost every turn (measured: 290 GB/s of stream; staged: see DESIGN.md).
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(Args a) {
   __shared__ unsigned long long list[kBlockCands];
-  __shared__ uint32_t cnt;
-  if (threadIdx.x == 0) cnt = 0;
+  __shared__ uint16_t list1[kStage1];
+  __shared__ uint32_t cnt, cnt1;
+  if (threadIdx.x == 0) { cnt = 0; cnt1 = 0; }
   __syncthreads();
   const unsigned long long lo = a.start + (unsigned long long)blockIdx.x * kScanBytes;
   const unsigned long long hi = lo + kScanBytes < a.n ? lo + kScanBytes : a.n;
   const uint8_t* s = a.s;
-  const uint32_t mis = (uint32_t)((uintptr_t)(s + lo) & 3);
-  const uint32_t* w = (const uint32_t*)(s + lo - mis);             // aligned view; position lo is byte `mis` of word 0
-  const unsigned long long last_word = (a.n - (lo - mis) - 1) >> 2;  // last word holding a stream byte
-  for (unsigned long long base = 0; lo + base < hi + mis; base += kScanThreads * 4) {
-    const unsigned long long k = (base >> 2) + threadIdx.x;         // this thread's word: view bytes [4k, 4k+4)
-    if (k > last_word) continue;
-    const uint32_t w0 = __ldg(w + k), w1 = k + 1 <= last_word ? __ldg(w + k + 1) : 0u;
+  // aligned word view of the whole stream: stream position p is view byte p + smis (aligned by construction)
+  const uint32_t smis = (uint32_t)((uintptr_t)s & 3);
+  const uint32_t* wb = (const uint32_t*)(s - smis);
+  const unsigned long long v_lo = lo + smis, v_hi = hi + smis;
+  const unsigned long long k_end = (v_hi + 3) >> 2, k_last = (a.n + smis - 1) >> 2;   // words of this CTA; last word holding a stream byte
+  unsigned long long k = (v_lo >> 2) + threadIdx.x;
+  uint32_t n0 = k < k_end ? __ldg(wb + k) : 0u, n1 = (k < k_end && k < k_last) ? __ldg(wb + k + 1) : 0u;
+  for (; k < k_end; k += kScanThreads) {
+    const uint32_t w0 = n0, w1 = n1;
+    {  // the next turn's words are on their way while this turn's four positions are tested
+      const unsigned long long kn = k + kScanThreads;
+      n0 = kn < k_end ? __ldg(wb + kn) : 0u;
+      n1 = (kn < k_end && kn < k_last) ? __ldg(wb + kn + 1) : 0u;
+    }
 #pragma unroll
-    for (uint32_t j = 0; j < 4; j++) {
+    for (uint32_t j = 0; j < 4; j++) {   // stage 1, registers only: type and length of "a header at this byte"
       const unsigned long long vb = 4 * k + j;                      // view byte index
-      if (vb < mis) continue;
-      const unsigned long long p = lo + (vb - mis);
-      if (p >= hi) continue;
+      if (vb < v_lo || vb >= v_hi) continue;
+      const unsigned long long p = vb - smis;
       const uint32_t hdr = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
-      const uint32_t id = hdr & 0xffu;
-      if (id > 1u && id < 0x80u) continue;
+      const uint32_t id = hdr & 0xffu, dlen = hdr >> 8;
       // A skippable chunk may announce any 24-bit length, so half of all random payload bytes would qualify in a large
       // stream.  Only short ones (identifier repeats, padding) are candidates; a stream with a longer skippable chunk
       // simply does not reach its end on the device and is walked by the host.
-      if (id >= 0x80u && (hdr >> 8) > kMaxSkippable) continue;
-      uint32_t kind, ul;
-      if (!header_ok(s, a.n, p, hdr, &kind, &ul)) continue;
-      // ... and so must its successor be (or the stream ends there).  Payload bytes that look like a header (JPEG data is
-      // full of ff 00 xx yy) almost never point at another plausible header.  A TRUE header in front of a malformed one
-      // is dropped by this too: the chain then stops short of the end, and the host walk reports the exact error.
-      const unsigned long long t = p + 4 + (hdr >> 8);
-      if (t != a.n) {
-        if (a.n - t < 4) continue;
-        uint32_t k2, u2;
-        if (!header_ok(s, a.n, t, load_hdr(s, t), &k2, &u2)) continue;
-      }
-      const uint32_t slot = atomicAdd(&cnt, 1u);
-      if (slot < kBlockCands) list[slot] = p;
+      const uint32_t dmax = id == 0u ? SNB_MAX_FRAME_DATA : (id == 1u ? kMaxBlock + 4u : kMaxSkippable);
+      if ((id > 1u && id < 0x80u) || dlen > dmax || (id <= 1u && dlen < 4u)) continue;
+      if (a.n - p < 4 || a.n - p - 4 < dlen) continue;
+      const uint32_t slot = atomicAdd(&cnt1, 1u);
+      if (slot < kStage1) list1[slot] = (uint16_t)(p - lo);
     }
+  }
+  __syncthreads();
+  const uint32_t c1 = cnt1;
+  if (c1 > kStage1) { if (threadIdx.x == 0) { a.sum->overflow = 1; a.blk_count[blockIdx.x] = 0; } return; }
+  // stage 2, one survivor per thread (no lane waits for another lane's rare path): the reference's full checks, and the
+  // next kHops headers the candidate leads to must pass them too (or the stream ends on the way).  Compressed payload is
+  // full of byte patterns that pass one test (00 / 01 are the tags of one-byte literals and short copies, ff 00 is JPEG
+  // stuffing): after one hop 0.7 % of the positions of a text stream still qualify, after three hardly any but the
+  // real headers.  A TRUE header within kHops chunks of a malformed one is dropped by this too: the chain then stops
+  // short of the end, and the host walk reports the exact error.
+  for (uint32_t i = threadIdx.x; i < c1; i += blockDim.x) {
+    const unsigned long long p = lo + list1[i];
+    uint32_t kind, ul;
+    const uint32_t hdr = load_hdr(s, p);
+    if (!header_ok(s, a.n, p, hdr, &kind, &ul)) continue;
+    unsigned long long t = p + 4 + (hdr >> 8);
+    bool chain_ok = true;
+    for (uint32_t hop = 0; hop < kHops && t != a.n; hop++) {
+      if (a.n - t < 4) { chain_ok = false; break; }
+      const uint32_t h2 = load_hdr(s, t);
+      uint32_t k2, u2;
+      if (((h2 & 0xffu) >= 0x80u && (h2 >> 8) > kMaxSkippable) || !header_ok(s, a.n, t, h2, &k2, &u2)) { chain_ok = false; break; }
+      t += 4 + (h2 >> 8);
+    }
+    if (!chain_ok) continue;
+    const uint32_t slot = atomicAdd(&cnt, 1u);
+    if (slot < kBlockCands) list[slot] = p;
   }
   __syncthreads();
   const uint32_t c = cnt;

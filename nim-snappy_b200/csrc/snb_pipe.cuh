@@ -263,6 +263,7 @@ __device__ __forceinline__ uint32_t compress_block_v6(const uint8_t* __restrict_
         if (hitmask) {
           int kh = __ffs((int)hitmask) - 1;
           uint32_t commit = (2u << kh) - 1u;
+          __syncwarp();   // every lane's table read of this step precedes the writes (WAR; the collectives above already imply it)
           if (((commit >> lane) & 1u) && ((grp & commit) >> lane) == 1u) table[h] = (uint16_t)pos;
           hit_ip = __shfl_sync(kFull, pos, kh);
           hit_cand = __shfl_sync(kFull, c, kh);
@@ -270,6 +271,7 @@ __device__ __forceinline__ uint32_t compress_block_v6(const uint8_t* __restrict_
           break;
         }
         if (vmask != kFull) break;
+        __syncwarp();
         if ((grp >> lane) == 1u) table[h] = (uint16_t)pos;
         wip = __shfl_sync(kFull, pos + step, 31);
         wskip = __shfl_sync(kFull, sk_after, 31);
@@ -354,6 +356,7 @@ __device__ __forceinline__ uint32_t compress_block_v6(const uint8_t* __restrict_
       if (stale) { SNB_STAT(5); force_slow = true; continue; }
       if (q0 >= 32) {
         SNB_STAT(6);
+        __syncwarp();
         if (((run >> lane) & 1u) && ((grp & run) >> lane) == 1u) table[h] = (uint16_t)p;
         k += (uint32_t)__popc(run);
         pp = b + bend;
@@ -438,6 +441,7 @@ __device__ __forceinline__ uint32_t compress_block_v6(const uint8_t* __restrict_
       if (ip == b + 32) ins |= 1u << 31; else pend_insert = true;
       m1_done = true;
     }
+    __syncwarp();
     if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[h] = (uint16_t)p;
     if (done) SNB_FINISH(ip);
     if (pend_insert) {

@@ -245,7 +245,10 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
   return r;
 }
 template <class T>
-static inline T __ldg(const T* p) { return *p; }
+static inline T __ldg(const T* p) {
+  if (((uintptr_t)p) % alignof(T) != 0) abort();   // the GPU faults on a misaligned load: so does the emulator
+  return *p;
+}
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
   unsigned long long o = *p; *p = o + v; return o;
