@@ -49,6 +49,30 @@ __device__ unsigned long long g_stats[16];
 #define SNB_STATN(i, n) do { } while (0)
 #endif
 
+// Optional critical-path timing of the window pass (diagnostic build -DSNB_CYC; never in the product build): cycles
+// between "value v has arrived" points, summed per warp in shared memory and flushed to g_cyc at the end of a block.
+#if defined(SNB_CYC) && !defined(SNB_EMULATE)
+__device__ unsigned long long g_cyc[16];
+__device__ __forceinline__ uint32_t cyc_after(uint32_t v) {   // %clock read that cannot issue before v is available
+  uint32_t t;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0x7fffffff;\n\t@p mov.u32 %0, %%clock;\n\t@!p mov.u32 %0, 0;\n\t}" : "=r"(t) : "r"(v) : "memory");
+  return t;
+}
+#define SNB_CYC_DECL __shared__ uint32_t cyc_acc[32][16]; const uint32_t cyc_w = threadIdx.x >> 5; uint32_t cyc_t = 0; \
+  if (lane < 16) cyc_acc[cyc_w][lane] = 0; __syncwarp(); const uint32_t cyc_begin = cyc_after(lane)
+#define SNB_CYC_START(v) cyc_t = cyc_after(v)
+#define SNB_CYC_MARK(i, v) do { const uint32_t n_ = cyc_after(v); if (lane == 0) cyc_acc[cyc_w][i] += n_ - cyc_t; cyc_t = n_; } while (0)
+#define SNB_CYC_COUNT(i) do { if (lane == 0) cyc_acc[cyc_w][i] += 1; } while (0)
+#define SNB_CYC_FLUSH() do { __syncwarp(); if (lane == 0) cyc_acc[cyc_w][15] = cyc_after(lane) - cyc_begin; __syncwarp(); \
+  if (lane < 16) atomicAdd(&g_cyc[lane], (unsigned long long)cyc_acc[cyc_w][lane]); } while (0)
+#else
+#define SNB_CYC_DECL do { } while (0)
+#define SNB_CYC_START(v) do { } while (0)
+#define SNB_CYC_MARK(i, v) do { } while (0)
+#define SNB_CYC_COUNT(i) do { } while (0)
+#define SNB_CYC_FLUSH() do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
@@ -337,26 +361,30 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
   bool m1_done = false;     // chain mode, ip on a window boundary: ip-1 has already been inserted
   constexpr uint32_t kNoWindow = 0xffffffffu;
   uint32_t Wn = 0, Wn_b = kNoWindow;   // prefetched own words of window Wn_b
+  SNB_CYC_DECL;
 
 #define SNB_FINISH(from)                                                          \
   do {                                                                            \
     uint32_t f_ = (from);                                                         \
     if (f_ < len) {                                                               \
       uint32_t n_ = len - f_;                                                     \
-      if (op + literal_size(n_) > abort_thr) return kAborted;                     \
+      if (op + literal_size(n_) > abort_thr) { SNB_CYC_FLUSH(); return kAborted; } \
       op += emit_literal_v2(out + op, v, f_, n_, lane);                           \
     }                                                                             \
+    SNB_CYC_FLUSH();                                                              \
     return op;                                                                    \
   } while (0)
 
   for (;;) {
     __syncwarp();  // table writes (zeroing / previous commit / serial step) visible to every lane
     const uint32_t b = (chain ? ip : pp) & ~31u;
+    SNB_CYC_START(b);
 
     SNB_STAT(8);
     if (force_slow || b + 32 >= ip_limit || (!chain && k >= 32)) {
       force_slow = false;
       m1_done = false;
+      SNB_CYC_COUNT(chain ? 9 : 10);
       if (chain) {
         SNB_STAT(1);
         // ---- one serial chain step straight on the table (encoder.nim:364-380)
@@ -445,6 +473,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     const uint32_t a0 = __funnelshift_r(w0, w1, own_s), a1 = __funnelshift_r(w1, w2, own_s), a2 = __funnelshift_r(w2, w3, own_s);
     const uint32_t h = hash14(a0, mask);
     const uint32_t T = table[h];
+    SNB_CYC_MARK(0, T);
     uint32_t ml;
     {
       uint32_t c0, c1, c2;
@@ -454,6 +483,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       const uint32_t base = x0 ? 0u : (x1 ? 4u : 8u);
       ml = xs ? base + first_diff_byte(xs) : 12u;
     }
+    SNB_CYC_MARK(1, ml);
     const uint32_t off = p - T;
     const bool c3 = off >= 2048;   // three-byte copy tag (ml <= 11 whenever the tag is used, encoder.nim:113-125)
     const uint32_t tb = c3 ? ((((ml - 1) << 2) | 2u) | (off << 8))
@@ -470,6 +500,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     // 128: no hit up to the window end (the literal run goes on)
     const uint32_t J = evt >= 32 ? 128u : (eml >= 12 ? 64u + evt : evt + eml);
     const uint32_t lkmask = notbelow & ((2u << umin32(evt, 31u)) - 1u);
+    SNB_CYC_MARK(2, J + lkmask + grp);
 #if SNB_V5_HINT
     // hint for the next window: its (pre-commit) table entries say where its candidates most likely are
     uint32_t Tn;
@@ -477,6 +508,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       const uint32_t n0 = __shfl_sync(kFull, Wn, (int)own_q), n1 = __shfl_sync(kFull, Wn, (int)own_q + 1);
       Tn = table[hash14(__funnelshift_r(n0, n1, own_s), mask)];
     }
+    SNB_CYC_MARK(3, Tn);
 #endif
 
     uint32_t ins = 0;      // lanes inserted in this pass
@@ -514,6 +546,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     }
 
     bool done = false;  // block finished inside this pass (ip > ip_limit after a copy)
+    SNB_CYC_MARK(4, c + ins);
     for (;;) {          // one batch per turn; a match that reaches the horizon ends a batch
       SNB_STAT(3);
       uint32_t A = 0, cc = c;
@@ -536,6 +569,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       ins |= insb;
       noprev = 0;
       SNB_STATN(7, __popc(A));
+      SNB_CYC_MARK(5, ins + stale);
       const uint32_t Ev = LK & HB;
       uint32_t EvT = Ev, tail = 0;
       if (cc >= 64 && cc < 96) EvT &= ~(1u << (cc - 64));                        // its copy is emitted below
@@ -554,6 +588,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
         }
       }
       op += (uint32_t)(__popc(LitB) + __popc(LS) + 2 * __popc(EvT) + __popc(E3));
+      SNB_CYC_MARK(6, op);
       if (op > abort_thr) return kAborted;
       if (slow_at < 32) { ip = b + slow_at; force_slow = true; break; }
       if (cc < 64) { ip = b + cc; break; }
@@ -569,6 +604,8 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       const uint32_t m = 12 + common_prefix_v2(v, len, cand + 12, b + e + 12, lane);
       op += emit_copy_v2(out + op, b + e - cand, m, lane);
       ip = b + e + m;
+      SNB_CYC_MARK(7, ip);
+      SNB_CYC_COUNT(11);
       if (op > abort_thr) return kAborted;
       if (ip > ip_limit) { done = true; break; }
       c = ip - b;
@@ -595,6 +632,8 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       const uint32_t d1 = in_ld4(v, ip - 1);
       if (lane == 0) table[hash14(d1, mask)] = (uint16_t)(ip - 1);
     }
+    SNB_CYC_MARK(8, ip + pp);
+    SNB_CYC_COUNT(12);
   }
 #undef SNB_FINISH
 }
@@ -1515,4 +1554,5 @@ __global__ void __launch_bounds__(32) raw_validate_kernel(RawWalkArgs a) {
 }  // namespace snb
 
 #include "snb_pipe.cuh"
+#include "snb_pair.cuh"
 #include "snb_frameidx.cuh"
