@@ -423,14 +423,14 @@ int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
     if (p) prof_mark(2, st);
     if (use_pair()) {
       // pairs per CTA: compress_warps with the table in shared memory (6 x 32 KiB + the CRC tables fill an SM), compress_gwarps more in L2
-      const uint32_t sp = (uint32_t)std::max(0, std::min({6, g.pair_spairs, (int)snb::pair::kMaxPairs}));
+      const uint32_t sp = (uint32_t)std::max(0, std::min({6, g.pair_spairs, (int)snb::pair::kMaxPairs}));   // groups of kRing warps
       const uint32_t gp = (uint32_t)std::max(0, std::min((int)(snb::pair::kMaxPairs - sp), g.pair_gpairs));
       const uint32_t np = std::max(1u, sp + gp);
       const size_t psmem = (size_t)sp * snb::kMaxTableEntries * 2 + np * sizeof(snb::pair::Box) + sizeof(snb::CrcSmem);
       const uint32_t pgrid = std::max(1u, std::min((cnt + np - 1) / np, (uint32_t)g.sms));
       CK(g.tables.ensure((size_t)pgrid * (np - sp) * snb::kMaxTableEntries * 2 + 256));
       a.c.smem_warps = sp; a.c.gtables = g.tables.as<uint16_t>();
-      SNB_LAUNCH(snb::compress_pair_kernel, pgrid, np * 64, psmem, st, a);
+      SNB_LAUNCH(snb::compress_pair_kernel, pgrid, np * 32 * snb::pair::kRing, psmem, st, a);
     } else if (use_pipe()) {
       const uint32_t pgrid = std::max(1u, std::min((cnt + snb::pipe::kGroups - 1) / snb::pipe::kGroups, (uint32_t)g.sms));
       SNB_LAUNCH(snb::compress_pipe_kernel, pgrid, snb::pipe::kThreads, snb::pipe::kSmemBytes, st, a);

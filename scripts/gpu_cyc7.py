@@ -18,7 +18,7 @@ d_in = torch.from_numpy(data).cuda()
 out = torch.empty(int(lib.snb_max_compressed_len_framed(n)), dtype=torch.uint8, device="cuda")
 dc.set_profiling(True)
 lib.snb_set_compress_algo(7)
-names = ["pre-resolve", "wait for turn", "->final ml", "->J", "->walk entry", "->walk+LK", "->emit/op", "long match", "->commit+verify", "->hand-over"]
+names = ["pre-resolve", "wait for the cursor", "fast: cursor -> handed over", "fast: emit + commit", "slow turn (all of it)"]
 for g in geoms:
     lib.snb_set_compress_warps(g)
     dc.compress_framed(d_in, out=out)
@@ -29,8 +29,8 @@ for g in geoms:
     lib.dll.snb_debug_cyc(v, 1)
     turns = max(1, v[12])
     chunks = n // 65536
-    print(f"== {g} pairs: {ms:.2f} ms -> {n / ms / 1e6:.1f} GB/s; turns/chunk {turns / chunks:.0f}, serial chain {v[13] / chunks:.0f}, serial lit {v[14] / chunks:.0f}, long {v[11] / chunks:.0f}")
+    print(f"== {g} pairs: {ms:.2f} ms -> {n / ms / 1e6:.1f} GB/s; turns/chunk {turns / chunks:.0f}, slow turns {v[10] / chunks:.0f}, serial chain {v[13] / chunks:.0f}, serial lit {v[14] / chunks:.0f}, long {v[11] / chunks:.0f}")
     for i, nm in enumerate(names):
         print(f"   {nm:20s} {v[i] / turns:8.1f} cyc/turn")
-    act = sum(v[2:10])
+    act = sum(v[2:5])
     print(f"   active part of a turn {act / turns:8.1f};  both warps' block time {v[15] / chunks / 2e3:.0f} kcyc/chunk = {v[15] / 2 / turns:.0f} cyc per turn", flush=True)
