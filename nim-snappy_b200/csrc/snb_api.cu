@@ -104,9 +104,7 @@ struct Ctx {
   uint32_t call_launches = 0;
   int compress_warps = 4;    // 64 KiB blocks: encoder warps per SM with the table in shared memory (more would squeeze the L1 below what the candidate loads need)
   int compress_gwarps = 18;  // ... and with the table in global memory (L2); 18 measured best on text (round 1f sweep), 20 on mixed data
-  int pair_spairs = 6;    // v7: warp pairs per CTA with the table in shared memory
-  int pair_gpairs = 0;    // v7: pairs per CTA beyond compress_warps, their tables in global memory
-  int compress_algo = 0;  // 0 auto (= 5: one warp per chunk, window walk on ballot masks), 6: resolver / walker warp groups (experimental)
+  int compress_algo = 0;  // reserved for A/B builds (one encoder is shipped: compress_block_v5, one warp per chunk)
   size_t l2_persist_max = 0, l2_window_max = 0;   // device limits for the L2 access-policy window (0: unsupported)
   int l2_tables = 0;                              // 1: persisting-L2 carve-out + access-policy window for the encoder's global-memory hash tables.
                                                   // Off by default: measured neutral outside a profiler (23.5 vs 23.8 ms / GiB), and under ncu the window is
@@ -217,7 +215,6 @@ int do_init(int device) {
   // tuning experiments only: persistent grids use this many SMs / chunks per slab of the host decode pipeline
   if (const char* e = getenv("SNB_TUNE_SMS")) g.sms = std::max(1, atoi(e));
   if (const char* e = getenv("SNB_TUNE_ALGO")) g.compress_algo = atoi(e);
-  if (const char* e = getenv("SNB_TUNE_PAIRS")) { g.pair_spairs = atoi(e) % 100; g.pair_gpairs = atoi(e) / 100; }
   if (const char* e = getenv("SNB_TUNE_DEC_SLAB")) g.dec_slab_chunks = (uint32_t)std::min<int>(kHostSlabChunks, std::max(1, atoi(e)));
 #ifndef SNB_EMULATE
   {
@@ -263,8 +260,6 @@ int do_init(int device) {
 #endif
   CK(cudaFuncSetAttribute(snb::compress_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
   CK(cudaFuncSetAttribute(snb::compress_kernel5, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
-  CK(cudaFuncSetAttribute(snb::compress_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
-  CK(cudaFuncSetAttribute(snb::compress_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
 #ifndef SNB_EMULATE
   {  // do launches block?  (second launch: the first one pays for loading the module)
     SNB_LAUNCH(snb::launch_probe_kernel, 1, 1, 0, g.s0, 0u);
@@ -321,8 +316,6 @@ void prof_collect(int first_pair, int n_pairs, int slot0) {
 
 // ---------------------------------------------------------------- launch geometry
 struct CompressGeom { uint32_t entries, warps, smem_warps, grid; size_t smem; };
-bool use_pair() { return g.compress_algo == 7; }   // warp pair per chunk (v7)
-bool use_pipe() { return g.compress_algo == 6; }   // ... with the resolver / walker kernel (v6): byte-exact, 2x algorithmic DRAM traffic, but 20 GB/s (walker-latency bound) -- not the default
 CompressGeom compress_geom(uint32_t max_len, uint32_t count) {
   CompressGeom cg;
   uint32_t e = 256;
@@ -421,20 +414,6 @@ int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
       a.span = g.d_span;
     }
     if (p) prof_mark(2, st);
-    if (use_pair()) {
-      // pairs per CTA: compress_warps with the table in shared memory (6 x 32 KiB + the CRC tables fill an SM), compress_gwarps more in L2
-      const uint32_t sp = (uint32_t)std::max(0, std::min({6, g.pair_spairs, (int)snb::pair::kMaxPairs}));   // groups of kRing warps
-      const uint32_t gp = (uint32_t)std::max(0, std::min((int)(snb::pair::kMaxPairs - sp), g.pair_gpairs));
-      const uint32_t np = std::max(1u, sp + gp);
-      const size_t psmem = (size_t)sp * snb::kMaxTableEntries * 2 + np * sizeof(snb::pair::Box) + sizeof(snb::CrcSmem);
-      const uint32_t pgrid = std::max(1u, std::min((cnt + np - 1) / np, (uint32_t)g.sms));
-      CK(g.tables.ensure((size_t)pgrid * (np - sp) * snb::kMaxTableEntries * 2 + 256));
-      a.c.smem_warps = sp; a.c.gtables = g.tables.as<uint16_t>();
-      SNB_LAUNCH(snb::compress_pair_kernel, pgrid, np * 32 * snb::pair::kRing, psmem, st, a);
-    } else if (use_pipe()) {
-      const uint32_t pgrid = std::max(1u, std::min((cnt + snb::pipe::kGroups - 1) / snb::pipe::kGroups, (uint32_t)g.sms));
-      SNB_LAUNCH(snb::compress_pipe_kernel, pgrid, snb::pipe::kThreads, snb::pipe::kSmemBytes, st, a);
-    } else
 #ifndef SNB_EMULATE
     if (const size_t tbytes = (size_t)cg.grid * (cg.warps - cg.smem_warps) * cg.entries * 2; g.l2_tables && g.l2_persist_max && g.l2_window_max && tbytes) {
       // the global-memory hash tables are the only randomly re-read data: pin them in L2, let everything else stream
@@ -1724,7 +1703,7 @@ uint64_t snb_debug_kernel_span_ns(void) {
   if (cudaMemcpy(v, g.d_span, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   return v[1] > v[0] ? v[1] - v[0] : 0;
 }
-void snb_set_compress_warps(int warps) { std::lock_guard<std::mutex> lk(g_mu); g.pair_spairs = g.compress_warps = warps % 100; if (warps >= 100) g.pair_gpairs = g.compress_gwarps = warps / 100 - 1; }
+void snb_set_compress_warps(int warps) { std::lock_guard<std::mutex> lk(g_mu); g.compress_warps = warps % 100; if (warps >= 100) g.compress_gwarps = warps / 100 - 1; }
 void snb_set_compress_algo(int algo) { std::lock_guard<std::mutex> lk(g_mu); g.compress_algo = algo; }
 void snb_set_arrive_timeout_ms(int ms) { std::lock_guard<std::mutex> lk(g_mu); g.arrive_timeout_ms = ms; }
 

@@ -6,7 +6,6 @@
 // What each routine reproduces (reference file:line, /root/reference @ 8ab5cf0):
 //   crc32c_warp          snappy/crc32c.c:204-214,676-763 + snappy/codec.nim:71-75 (maskedCrc)
 //   compress_block_v5    snappy/encoder.nim:184-383 (encodeBlock), :44-73, :81-125, :130-182
-//   compress_block_v6    the same parse split over resolver warps and a walker warp (snb_pipe.cuh, experimental)
 //   fidx::*              snappy.nim:199-265 header walk on the device (snb_frameidx.cuh)
 //   compress_job         snappy/encoder.nim:385-426 (encodeFrame) / snappy.nim:27-64 (compress)
 //   decompress_warp      snappy.nim:84-110 (uncompress) + snappy/decoder.nim:20-155 (decodeAllTags)
@@ -390,7 +389,9 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
   bool m1_done = false;     // chain mode, ip on a window boundary: ip-1 has already been inserted
   constexpr uint32_t kNoWindow = 0xffffffffu;
   uint32_t Wn = 0, Wn_b = kNoWindow;   // prefetched own words of window Wn_b (the next window) ...
+#if SNB_V5_WDEPTH2
   uint32_t Wm = 0, Wm_b = kNoWindow;   // ... and of the one after it: the hint below reads Wn, which must not be a load in flight
+#endif
 #if SNB_V5_OPT == 0
   const bool never_opt = true;
 #elif SNB_V5_OPT == 1 && !defined(SNB_EMULATE)
@@ -1655,6 +1656,4 @@ __global__ void __launch_bounds__(32) raw_validate_kernel(RawWalkArgs a) {
 
 }  // namespace snb
 
-#include "snb_pipe.cuh"
-#include "snb_pair.cuh"
 #include "snb_frameidx.cuh"
