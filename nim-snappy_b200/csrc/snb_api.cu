@@ -1545,11 +1545,19 @@ int snb_dev_uncompress_framed(const uint8_t* d_stream, uint64_t n, uint8_t* d_ou
   *read = 0; *written = 0;
   CKS(need_init());
   cudaStream_t st = (cudaStream_t)stream;
+  const bool dbg = getenv("SNB_DEBUG_DEVUNC") != nullptr;   // host-side timeline on stderr
+  const auto t0 = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (dbg) fprintf(stderr, "snb_dev_uncompress_framed: %8.1f us  %s\n",
+                     std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), what);
+  };
   CKS(dev_begin(st));
   prof_begin();
   if (g.profiling) for (int i = 0; i < 6; i++) g.prof[i] = 0;
+  tick("begin");
   DevIndex r;
   CKS(dev_frame_index(d_stream, n, out_cap, check_header, check_integrity, d_frame_lens, n_frames, nullptr, 0, st, r));
+  tick("frame index done (synchronised)");
   const size_t count = r.n_chunks;
   std::vector<int32_t> status(count);
   if (count) {
@@ -1559,7 +1567,9 @@ int snb_dev_uncompress_framed(const uint8_t* d_stream, uint64_t n, uint8_t* d_ou
     CKS(launch_decompress(d_stream, d_out, r.d_chunks, (uint32_t)count, check_integrity, g.status.as<int32_t>(),
                           g.outlen.as<uint32_t>(), st));
     CK(cudaMemcpyAsync(status.data(), g.status.p, count * 4, cudaMemcpyDeviceToHost, st));
+    tick("decode launched");
     CK(cudaStreamSynchronize(st));
+    tick("decode done");
     prof_collect(8, 1, 4);
   }
   g.prof[5] = (float)g.call_launches;

@@ -95,37 +95,11 @@ __device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 #endif
-#ifndef SNB_V5_TABLE_HINT
-#define SNB_V5_TABLE_HINT 0   // 1: global-memory hash tables are read / written with L2::evict_last
-#endif
-#if SNB_V5_TABLE_HINT && !defined(SNB_EMULATE)
-__device__ __forceinline__ unsigned long long tab_policy() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ uint32_t tab_ld(const uint16_t* p, bool sh) {
-  if (sh) return *p;
-  uint16_t v;
-  asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(tab_policy()) : "memory");
-  return v;
-}
-__device__ __forceinline__ void tab_st(uint16_t* p, uint32_t v, bool sh) {
-  if (sh) { *p = (uint16_t)v; return; }
-  asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"((uint16_t)v), "l"(tab_policy()) : "memory");
-}
-#else
-__device__ __forceinline__ uint32_t tab_ld(const uint16_t* p, bool) { return *p; }
-__device__ __forceinline__ void tab_st(uint16_t* p, uint32_t v, bool) { *p = (uint16_t)v; }
-#endif
 #ifndef SNB_CRC_AFTER
 #define SNB_CRC_AFTER 0
 #endif
 #ifndef SNB_V5_WDEPTH2
-#define SNB_V5_WDEPTH2 0   // own words prefetched two windows ahead (the hint reads the next window's words)
-#endif
-#ifndef SNB_V5_OPT
-#define SNB_V5_OPT 0       // optimistic commit without match.any: 0 never, 1 warps whose table is in shared memory, 2 always
+#define SNB_V5_WDEPTH2 0   // 1: own words prefetched two windows ahead, so the hint never reads a load in flight (measured: 45.1 -> 44.4 GB/s)
 #endif
 #ifndef SNB_V5_HINT
 #define SNB_V5_HINT 1   // 0: none, 1: L1 hint, 2: L2 hint for the next window's candidates
@@ -337,6 +311,26 @@ __device__ __forceinline__ void in_ld12u(const InView& v, uint32_t p, uint32_t& 
   uint32_t w0 = __ldg(v.w + k), w1 = __ldg(v.w + k + 1), w2 = __ldg(v.w + k + 2), w3 = __ldg(v.w + umin32(k + 3, v.last));
   b0 = __funnelshift_r(w0, w1, s); b1 = __funnelshift_r(w1, w2, s); b2 = __funnelshift_r(w2, w3, s);
 }
+// The same 12 bytes through 16-byte aligned loads: one LDG.128, and a second one only in the lanes whose bytes
+// straddle it (1.7 load instructions per lane instead of 4).  Reads stay inside the 16-byte aligned envelope of
+// [in, in + len).  A/B switch, off: see SNB_V5_CAND128.
+#ifndef SNB_V5_CAND128
+#define SNB_V5_CAND128 0   // measured neutral (45.25 -> 45.42 GB/s): the tag stage is at 23 %, not the limiter the sector count suggested
+#endif
+__device__ __forceinline__ void in_ld12a(const InView& v, uint32_t p, uint32_t& b0, uint32_t& b1, uint32_t& b2) {
+  const uintptr_t addr = (uintptr_t)v.w + v.mis + p;
+  const uint4* a16 = (const uint4*)(addr & ~(uintptr_t)15);
+  const uint32_t q = (uint32_t)(addr & 15);
+  const uint4 X = __ldg(a16);
+  uint4 Y; Y.x = Y.y = Y.z = Y.w = 0;
+  if (q > 4) Y = __ldg(a16 + 1);
+  const bool hi2 = (q & 8) != 0, hi1 = (q & 4) != 0;
+  // the five words from word (q >> 2) & 2 on, then the four from word q >> 2 on
+  const uint32_t p0 = hi2 ? X.z : X.x, p1 = hi2 ? X.w : X.y, p2 = hi2 ? Y.x : X.z, p3 = hi2 ? Y.y : X.w, p4 = hi2 ? Y.z : Y.x;
+  const uint32_t w0 = hi1 ? p1 : p0, w1 = hi1 ? p2 : p1, w2 = hi1 ? p3 : p2, w3 = hi1 ? p4 : p3;
+  const uint32_t sh = (q & 3) * 8;
+  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
+}
 // --------------------------------------------------------------------- encodeBlock, v5
 // Window walk on ballot masks.  One pass handles the 32 positions [b, b+32) that hold the cursor:
 //
@@ -388,23 +382,10 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
   bool chain = false, force_slow = false;
   bool m1_done = false;     // chain mode, ip on a window boundary: ip-1 has already been inserted
   constexpr uint32_t kNoWindow = 0xffffffffu;
-  uint32_t Wn = 0, Wn_b = kNoWindow;   // prefetched own words of window Wn_b (the next window) ...
+  uint32_t Wn = 0, Wn_b = kNoWindow;   // prefetched own words of window Wn_b
 #if SNB_V5_WDEPTH2
-  uint32_t Wm = 0, Wm_b = kNoWindow;   // ... and of the one after it: the hint below reads Wn, which must not be a load in flight
+  uint32_t Wm = 0, Wm_b = kNoWindow;   // ... and of the window after it
 #endif
-#if SNB_V5_OPT == 0
-  const bool never_opt = true;
-#elif SNB_V5_OPT == 1 && !defined(SNB_EMULATE)
-  const bool never_opt = !__isShared(table);   // reading an entry back right after writing it is an L2 round trip for a global table
-#else
-  const bool never_opt = false;
-#endif
-#ifdef SNB_EMULATE
-  const bool tsh = true;
-#else
-  const bool tsh = __isShared(table);
-#endif
-  bool exact = never_opt;              // this pass runs the exact conflict handling (always, or after an optimistic attempt failed)
   SNB_CYC_DECL;
 
 #define SNB_FINISH(from)                                                          \
@@ -499,14 +480,6 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     }
 
     // ---- window [b, b+32): every lane is a valid lookup position (b + 32 < ip_limit)
-    // The pass first runs optimistically: no hash groups (match.any costs 200-390 cycles on sm_100a and a conflict
-    // shows up in about 4 % of the passes), every inserted lane writes the table, the entries are read back, and if
-    // two inserted lanes did share a hash the entries are restored and the pass is redone on the exact path.
-    const uint32_t s_ip = ip, s_pp = pp, s_k = k, s_ne = next_emit, s_op = op;
-    const bool s_chain = chain, s_m1 = m1_done;
-#define SNB_REDO_EXACT()                                                                                  \
-  do { ip = s_ip; pp = s_pp; k = s_k; next_emit = s_ne; op = s_op; chain = s_chain; m1_done = s_m1;      \
-       force_slow = false; exact = true; SNB_STAT(13); } while (0)
     const uint32_t p = b + lane;
     if (chain && ip == b && !m1_done) {  // arrival on the window boundary after a serial step: ip-1 is not a lane here
       const uint32_t d1 = in_ld4(v, ip - 1);
@@ -531,12 +504,16 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     const uint32_t w2 = __shfl_sync(kFull, W, (int)own_q + 2), w3 = __shfl_sync(kFull, W, (int)own_q + 3);
     const uint32_t a0 = __funnelshift_r(w0, w1, own_s), a1 = __funnelshift_r(w1, w2, own_s), a2 = __funnelshift_r(w2, w3, own_s);
     const uint32_t h = hash14(a0, mask);
-    const uint32_t T = tab_ld(table + h, tsh);
+    const uint32_t T = table[h];
     SNB_CYC_MARK(0, T);
     uint32_t ml;
     {
       uint32_t c0, c1, c2;
+#if SNB_V5_CAND128
+      in_ld12a(v, T, c0, c1, c2);
+#else
       in_ld12u(v, T, c0, c1, c2);
+#endif
       const uint32_t x0 = a0 ^ c0, x1 = a1 ^ c1, x2 = a2 ^ c2;
       const uint32_t xs = x0 ? x0 : (x1 ? x1 : x2);
       const uint32_t base = x0 ? 0u : (x1 ? 4u : 8u);
@@ -547,8 +524,8 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     const bool c3 = off >= 2048;   // three-byte copy tag (ml <= 11 whenever the tag is used, encoder.nim:113-125)
     const uint32_t tb = c3 ? ((((ml - 1) << 2) | 2u) | (off << 8))
                            : ((((off >> 8) << 5) | ((ml - 4) << 2) | 1u) | ((off & 0xff) << 8));
-    const uint32_t grp = exact ? __match_any_sync(kFull, h) : (1u << lane);
-    const uint32_t eg = grp & below;                   // earlier lanes of my hash group (exact pass only)
+    const uint32_t grp = __match_any_sync(kFull, h);
+    const uint32_t eg = grp & below;                   // earlier lanes of my hash group
     const uint32_t HB = __ballot_sync(kFull, ml >= 4);
     const uint32_t C3 = __ballot_sync(kFull, c3);
     // every lane as a chain arrival: its event lane, the looked-up lanes, the next arrival
@@ -565,7 +542,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     uint32_t Tn;
     {
       const uint32_t n0 = __shfl_sync(kFull, Wn, (int)own_q), n1 = __shfl_sync(kFull, Wn, (int)own_q + 1);
-      Tn = tab_ld(table + hash14(__funnelshift_r(n0, n1, own_s), mask), tsh);
+      Tn = table[hash14(__funnelshift_r(n0, n1, own_s), mask)];
     }
     SNB_CYC_MARK(3, Tn);
 #endif
@@ -573,7 +550,6 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     uint32_t ins = 0;      // lanes inserted in this pass
     uint32_t c = 0;        // entry arrival lane
     uint32_t noprev = 0;   // arrival whose predecessor lane is not inserted again (a probe hit)
-    bool redo = false;
     if (!chain) {
       // ---- the literal run entering the window: stride-1 probes at lanes [l0, bend)
       const uint32_t l0 = pp - b;
@@ -582,37 +558,19 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       const uint32_t qh = HB & range;
       const uint32_t q0 = qh ? (uint32_t)__ffs((int)qh) - 1u : 32u;
       const uint32_t run = range & (q0 >= 32 ? 0xffffffffu : ((2u << q0) - 1u));   // probes performed
-      if (exact) {
-        const uint32_t stale = __ballot_sync(kFull, (eg & run) != 0) & run;
-        if (stale) { SNB_STAT(5); force_slow = true; exact = never_opt; continue; }
-      }
+      const uint32_t stale = __ballot_sync(kFull, (eg & run) != 0) & run;
+      if (stale) { SNB_STAT(5); force_slow = true; continue; }
       if (q0 >= 32) {  // every probe missed: insert them and move on (k == 32 switches to the strided scan)
         SNB_STAT(6);
         __syncwarp();
-        const bool mine = (run >> lane) & 1u;
-        if (exact) {
-          if (mine && ((grp & run) >> lane) == 1u) table[h] = (uint16_t)p;
-        } else {
-          if (mine) table[h] = (uint16_t)p;
-          __syncwarp();
-          if (__any_sync(kFull, mine && *(const volatile uint16_t*)(table + h) != p)) {   // two probes share a hash: take it back
-            __syncwarp();
-            if (mine) table[h] = (uint16_t)T;
-            SNB_REDO_EXACT();
-            continue;
-          }
-        }
-        exact = never_opt;
+        if (((run >> lane) & 1u) && ((grp & run) >> lane) == 1u) table[h] = (uint16_t)p;
         k += (uint32_t)__popc(run);
         pp = b + bend;
         continue;
       }
       {  // :336-338; the copy at q0 is the first event of the walk
         const uint32_t n = b + q0 - next_emit;
-        if (op + literal_size(n) > abort_thr) {
-          if (!exact) { SNB_REDO_EXACT(); continue; }
-          return kAborted;
-        }
+        if (op + literal_size(n) > abort_thr) return kAborted;
         op += emit_literal_v2(out + op, v, next_emit, n, lane);
       }
       ins = run;
@@ -632,19 +590,17 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       bool onp = (A >> lane) & 1u;
       uint32_t LK = __reduce_or_sync(kFull, onp ? lkmask : 0u);
       uint32_t insb = LK | ((A & ~noprev) >> 1);
+      const uint32_t stale = __ballot_sync(kFull, ((LK >> lane) & 1u) && (eg & (ins | insb)) != 0);
       uint32_t slow_at = 32;
-      if (exact) {
-        const uint32_t stale = __ballot_sync(kFull, ((LK >> lane) & 1u) && (eg & (ins | insb)) != 0);
-        if (stale) {  // keep the arrivals whose lookups all precede the first stale lane
-          SNB_STAT(9);
-          const uint32_t xs = (uint32_t)__ffs((int)stale) - 1u;
-          slow_at = 31u - (uint32_t)__clz((int)(A & ((2u << xs) - 1u)));
-          A &= (1u << slow_at) - 1u;
-          onp = (A >> lane) & 1u;
-          LK = __reduce_or_sync(kFull, onp ? lkmask : 0u);
-          insb = LK | ((A & ~noprev) >> 1);
-          cc = 32;
-        }
+      if (stale) {  // keep the arrivals whose lookups all precede the first stale lane
+        SNB_STAT(9);
+        const uint32_t xs = (uint32_t)__ffs((int)stale) - 1u;
+        slow_at = 31u - (uint32_t)__clz((int)(A & ((2u << xs) - 1u)));
+        A &= (1u << slow_at) - 1u;
+        onp = (A >> lane) & 1u;
+        LK = __reduce_or_sync(kFull, onp ? lkmask : 0u);
+        insb = LK | ((A & ~noprev) >> 1);
+        cc = 32;
       }
       ins |= insb;
       noprev = 0;
@@ -669,10 +625,7 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       }
       op += (uint32_t)(__popc(LitB) + __popc(LS) + 2 * __popc(EvT) + __popc(E3));
       SNB_CYC_MARK(6, op);
-      if (op > abort_thr) {
-        if (!exact) { redo = true; break; }
-        return kAborted;
-      }
+      if (op > abort_thr) return kAborted;
       if (slow_at < 32) { ip = b + slow_at; force_slow = true; break; }
       if (cc < 64) { ip = b + cc; break; }
       if (cc == 128) {
@@ -689,15 +642,11 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       ip = b + e + m;
       SNB_CYC_MARK(7, ip);
       SNB_CYC_COUNT(11);
-      if (op > abort_thr) {
-        if (!exact) { redo = true; break; }
-        return kAborted;
-      }
+      if (op > abort_thr) return kAborted;
       if (ip > ip_limit) { done = true; break; }
       c = ip - b;
       if (c >= 32) break;
     }
-    if (redo) { SNB_REDO_EXACT(); continue; }
     if (chain && !force_slow && ip > ip_limit) done = true;   // encoder.nim:362-363
     // the next arrival's ip-1 insert when no window pass will own it (lane c-1 of the arrival rule)
     bool pend_insert = false;
@@ -710,24 +659,9 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
 #elif SNB_V5_HINT == 2
     prefetch_l2(v.w + ((Tn + v.mis) >> 2));
 #endif
-    // ---- commit
+    // ---- commit: the last inserted lane of each hash group writes the table
     __syncwarp();   // after every lane's reads of this pass (WAR: racecheck-clean; the ballots above already order them in practice)
-    {
-      const bool mine = (ins >> lane) & 1u;
-      if (exact) {   // the last inserted lane of each hash group writes the table
-        if (mine && ((grp & ins) >> lane) == 1u) tab_st(table + h, p, tsh);
-      } else {       // every inserted lane writes; two of them sharing a hash show up as a lost write
-        if (mine) table[h] = (uint16_t)p;
-        __syncwarp();
-        if (__any_sync(kFull, mine && *(const volatile uint16_t*)(table + h) != p)) {
-          __syncwarp();
-          if (mine) table[h] = (uint16_t)T;   // every lane of a group read the same entry
-          SNB_REDO_EXACT();
-          continue;
-        }
-      }
-      exact = never_opt;
-    }
+    if (((ins >> lane) & 1u) && ((grp & ins) >> lane) == 1u) table[h] = (uint16_t)p;
     if (done) SNB_FINISH(ip);
     if (pend_insert) {
       __syncwarp();
@@ -738,7 +672,6 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     SNB_CYC_COUNT(12);
   }
 #undef SNB_FINISH
-#undef SNB_REDO_EXACT
 }
 
 struct CompressArgs {
@@ -1216,10 +1149,13 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
   const uint32_t tmis = (uint32_t)((uintptr_t)tags & 3);
   const uint32_t* const tw = (const uint32_t*)(tags - tmis);
   const uint32_t tw_last = (tn + tmis - 1) >> 2;   // tn >= 1 here
-  // 256 stream bytes held in registers: lane l has words kb + l (Wa) and kb + 32 + l (Wb); Wb is fetched
-  // long before the cursor reaches it, so a step never waits for the stream
+  // 256 stream bytes held in registers: lane l has words kb + l (Wa) and kb + 32 + l (Wb).  The row after them
+  // (Wc) is already on its way: the shuffles below read Wa and Wb in every step, so a row that has only just been
+  // requested when the window slides would stall the warp for a DRAM round trip every 128 stream bytes
+  // (25 % of the stall samples in profiles/r2_decompress_kernel_1GiB.txt)
   uint32_t kb = 0;
   uint32_t Wa = __ldg(tw + umin32(lane, tw_last)), Wb = __ldg(tw + umin32(32 + lane, tw_last));
+  uint32_t Wc = __ldg(tw + umin32(64 + lane, tw_last));
   // short elements (<= 16 bytes) of the previous step: sources already loaded, stores still to do.  They are
   // flushed after the next step's tag parse, so the source loads never stall the warp.
   uint32_t pL = 0, pdst = 0, pssh = 0, px0 = 0, px1 = 0, px2 = 0, px3 = 0, px4 = 0;
@@ -1246,9 +1182,9 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     {
       const uint32_t k0 = i0 >> 2;
       if (k0 - kb >= 32) {
-        if (k0 - kb < 64) { Wa = Wb; kb += 32; }
-        else { kb = k0; Wa = __ldg(tw + umin32(kb + lane, tw_last)); }
-        Wb = __ldg(tw + umin32(kb + 32 + lane, tw_last));
+        if (k0 - kb < 64) { Wa = Wb; Wb = Wc; kb += 32; }
+        else { kb = k0; Wa = __ldg(tw + umin32(kb + lane, tw_last)); Wb = __ldg(tw + umin32(kb + 32 + lane, tw_last)); }
+        Wc = __ldg(tw + umin32(kb + 64 + lane, tw_last));
       }
     }
     const uint32_t j = ((i0 >> 2) - kb) + (((i0 & 3) + lane) >> 2), sh = (((i0 & 3) + lane) & 3) * 8;
