@@ -113,35 +113,44 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(Args a) {
   const unsigned long long lo = a.start + (unsigned long long)blockIdx.x * kScanBytes;
   const unsigned long long hi = lo + kScanBytes < a.n ? lo + kScanBytes : a.n;
   const uint8_t* s = a.s;
-  // aligned word view of the whole stream: stream position p is view byte p + smis (aligned by construction)
-  const uint32_t smis = (uint32_t)((uintptr_t)s & 3);
-  const uint32_t* wb = (const uint32_t*)(s - smis);
+  // 16-byte aligned view of the whole stream: stream position p is view byte p + smis.  A thread takes 16 positions per
+  // turn (one LDG.128 plus the word after it), the tests run on 32-bit offsets relative to the CTA's first position.
+  const uint32_t smis = (uint32_t)((uintptr_t)s & 15);
+  const uint4* vb = (const uint4*)(s - smis);
   const unsigned long long v_lo = lo + smis, v_hi = hi + smis;
-  const unsigned long long k_end = (v_hi + 3) >> 2, k_last = (a.n + smis - 1) >> 2;   // words of this CTA; last word holding a stream byte
-  unsigned long long k = (v_lo >> 2) + threadIdx.x;
-  uint32_t n0 = k < k_end ? __ldg(wb + k) : 0u, n1 = (k < k_end && k < k_last) ? __ldg(wb + k + 1) : 0u;
-  for (; k < k_end; k += kScanThreads) {
-    const uint32_t w0 = n0, w1 = n1;
-    {  // the next turn's words are on their way while this turn's four positions are tested
-      const unsigned long long kn = k + kScanThreads;
-      n0 = kn < k_end ? __ldg(wb + kn) : 0u;
-      n1 = (kn < k_end && kn < k_last) ? __ldg(wb + kn + 1) : 0u;
+  const unsigned long long u0 = v_lo >> 4;                                  // first 16-byte unit of this CTA
+  const uint32_t nunits = hi > lo ? (uint32_t)(((v_hi + 15) >> 4) - u0) : 0u;
+  const unsigned long long u_last = (a.n + smis - 1) >> 4;                  // last unit holding a stream byte
+  const uint32_t rel0 = (uint32_t)(v_lo & 15);                              // where `lo` sits inside the first unit
+  const uint32_t span = (uint32_t)(hi - lo);                                // positions of this CTA
+  const unsigned long long rem64 = a.n - lo;
+  const uint32_t rem = rem64 > 0xffffffffull ? 0xffffffffu : (uint32_t)rem64;   // stream bytes from `lo` on (clamped: lengths are 24 bits)
+  uint32_t u = threadIdx.x;
+  uint4 nX; nX.x = nX.y = nX.z = nX.w = 0;
+  uint32_t n4 = 0;
+  if (u < nunits) { nX = __ldg(vb + u0 + u); n4 = (u0 + u < u_last) ? __ldg((const uint32_t*)(vb + u0 + u + 1)) : 0u; }
+  for (; u < nunits; u += kScanThreads) {
+    const uint32_t w[5] = {nX.x, nX.y, nX.z, nX.w, n4};
+    {  // the next turn's bytes are on their way while this turn's sixteen positions are tested
+      const uint32_t un = u + kScanThreads;
+      if (un < nunits) { nX = __ldg(vb + u0 + un); n4 = (u0 + un < u_last) ? __ldg((const uint32_t*)(vb + u0 + un + 1)) : 0u; }
     }
 #pragma unroll
-    for (uint32_t j = 0; j < 4; j++) {   // stage 1, registers only: type and length of "a header at this byte"
-      const unsigned long long vb = 4 * k + j;                      // view byte index
-      if (vb < v_lo || vb >= v_hi) continue;
-      const unsigned long long p = vb - smis;
-      const uint32_t hdr = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
+    for (uint32_t j = 0; j < 16; j++) {   // stage 1, registers only: type and length of "a header at this byte"
+      const uint32_t r = 16 * u + j - rel0;                         // position relative to `lo`; wraps for the bytes before it
+      if (r >= span) continue;
+      const uint32_t hdr = (j & 3) ? __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3)) : w[j >> 2];
       const uint32_t id = hdr & 0xffu, dlen = hdr >> 8;
       // A skippable chunk may announce any 24-bit length, so half of all random payload bytes would qualify in a large
       // stream.  Only short ones (identifier repeats, padding) are candidates; a stream with a longer skippable chunk
       // simply does not reach its end on the device and is walked by the host.
-      const uint32_t dmax = id == 0u ? SNB_MAX_FRAME_DATA : (id == 1u ? kMaxBlock + 4u : kMaxSkippable);
-      if ((id > 1u && id < 0x80u) || dlen > dmax || (id <= 1u && dlen < 4u)) continue;
-      if (a.n - p < 4 || a.n - p - 4 < dlen) continue;
+      const bool ok = id <= 1u ? (dlen - 4u <= (id == 0u ? SNB_MAX_FRAME_DATA - 4u : kMaxBlock))
+                               : (id >= 0x80u && dlen <= kMaxSkippable);
+      if (!ok) continue;
+      const uint32_t left = rem - r;                                // stream bytes from this position on
+      if (left < 4 || left - 4 < dlen) continue;
       const uint32_t slot = atomicAdd(&cnt1, 1u);
-      if (slot < kStage1) list1[slot] = (uint16_t)(p - lo);
+      if (slot < kStage1) list1[slot] = (uint16_t)r;
     }
   }
   __syncthreads();
