@@ -597,6 +597,12 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "snb::compress_stream_kernel (CRC + encode + in-order pack, one launch per slab)", "how": "algorithmic bytes (U + C) / kernel time from CUDA events on the launching stream inside the timed loop", "achieved": round(alg_bytes / (ck_ms * 1e-3) / 1e9, 3),
                      "peak": peak, "unit": "GB/s", "frac": round(alg_bytes / (ck_ms * 1e-3) / 1e9 / peak, 5),
                      "traffic": (traffic or {}).get("compress_kernel_bytes_per_launch"),
+                     # what the DRAM actually moves for this kernel (ncu capture of the same 1 GiB launch / the live kernel time):
+                     # random 32-byte sectors of 3 256 chunk histories + hash tables, which the HBM sustains at 1.39 TB/s
+                     # (profiles/r2d_ubench_random_sectors.txt), not at the sequential figure `peak` is -- DESIGN.md §4
+                     "dram_traffic_gbs": (round(traffic["compress_kernel_bytes_per_launch"] / (ck_ms * 1e-3) / 1e9, 1)
+                                          if traffic and n == (1 << 30) else None),
+                     "dram_random_sector_peak_gbs": 1390.0,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": round(ck_ms, 4), "peak_source": peak_src,
                      "step_kernels_ms": {k: round(v / args.steps, 4) for k, v in kern_ms.items()}},
         "e2e": {"value": round(total_in / e2e_c / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": int(n),
