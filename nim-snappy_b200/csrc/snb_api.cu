@@ -85,7 +85,7 @@ struct Ctx {
   uint64_t* d_total = nullptr;  // 4 device scalars
   unsigned long long* d_span = nullptr;   // 2 device scalars: in-kernel %globaltimer span of the last streaming compress kernel (debug)
   bool span_on = false;
-  DevBuf scratch, lens, offs, crcs, chunks, status, outlen, tables, in[4], out[4];
+  DevBuf scratch, lens, offs, crcs, chunks, status, outlen, order, tables, in[4], out[4];
   PinBuf h_in[4], h_out[4], h_meta[4];
   DevBuf group_done, group_end;     // streaming compress: per-group placement counters / end offsets
   uint64_t raw_block_decodes = 0;
@@ -104,6 +104,7 @@ struct Ctx {
   uint32_t call_launches = 0;
   int compress_warps = 4;    // 64 KiB blocks: encoder warps per SM with the table in shared memory (more would squeeze the L1 below what the candidate loads need)
   int compress_gwarps = 18;  // ... and with the table in global memory (L2); 18 measured best on text (round 1f sweep), 20 on mixed data
+  int dec_lpt = 1;        // device-resident decode launches: largest compressed chunks first (SNB_TUNE_DEC_LPT=0: stream order)
   int compress_algo = 0;  // reserved for A/B builds (one encoder is shipped: compress_block_v5, one warp per chunk)
   size_t l2_persist_max = 0, l2_window_max = 0;   // device limits for the L2 access-policy window (0: unsupported)
   int l2_tables = 0;                              // 1: persisting-L2 carve-out + access-policy window for the encoder's global-memory hash tables.
@@ -215,6 +216,7 @@ int do_init(int device) {
   // tuning experiments only: persistent grids use this many SMs / chunks per slab of the host decode pipeline
   if (const char* e = getenv("SNB_TUNE_SMS")) g.sms = std::max(1, atoi(e));
   if (const char* e = getenv("SNB_TUNE_ALGO")) g.compress_algo = atoi(e);
+  if (const char* e = getenv("SNB_TUNE_DEC_LPT")) g.dec_lpt = atoi(e);
   if (const char* e = getenv("SNB_TUNE_DEC_SLAB")) g.dec_slab_chunks = (uint32_t)std::min<int>(kHostSlabChunks, std::max(1, atoi(e)));
 #ifndef SNB_EMULATE
   {
@@ -442,11 +444,19 @@ int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
 }
 
 int launch_decompress(const uint8_t* d_in, uint8_t* d_out, const snb::Chunk* d_chunks, uint32_t count, int verify,
-                      int32_t* d_status, uint32_t* d_outlen, cudaStream_t st) {
+                      int32_t* d_status, uint32_t* d_outlen, cudaStream_t st, bool lpt = false) {
   if (!count) return SNB_OK;
   snb::DecompressArgs a;
   a.in_base = d_in; a.out_base = d_out; a.chunks = d_chunks; a.status = d_status; a.out_len = d_outlen;
   a.count = count; a.verify = verify ? 1u : 0u;
+  a.order = nullptr;
+  // more chunks than resident warps: start the expensive ones first, so that the launch does not end on them
+  if (lpt && g.dec_lpt && count > (uint32_t)g.sms * snb::kDecBlocksPerSm * (snb::kDecThreads / 32)) {
+    CK(g.order.ensure((size_t)count * 4));
+    SNB_LAUNCH(snb::decode_order_kernel, 1, 1024, 0, st, d_chunks, count, g.order.as<uint32_t>());
+    count_launch();
+    a.order = g.order.as<uint32_t>();
+  }
   CKS(next_counter(st, &a.counter));
   const uint32_t wpb = snb::kDecThreads / 32;
   uint32_t grid = std::max(1u, std::min((count + wpb - 1) / wpb, (uint32_t)g.sms * snb::kDecBlocksPerSm * 2));
@@ -1303,7 +1313,7 @@ void snb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.ready) return;
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.tables, &g.group_done, &g.group_end, &g.raw_in, &g.raw_walk})
+  for (DevBuf* b : {&g.scratch, &g.lens, &g.offs, &g.crcs, &g.chunks, &g.status, &g.outlen, &g.order, &g.tables, &g.group_done, &g.group_end, &g.raw_in, &g.raw_walk})
     b->release();
   for (int i = 0; i < 4; i++) { g.in[i].release(); g.out[i].release(); g.h_in[i].release(); g.h_out[i].release(); g.h_meta[i].release(); }
   for (PinBuf* b : {&g.h_flags[0], &g.h_flags[1], &g.h_arr}) b->release();
@@ -1511,7 +1521,7 @@ int snb_dev_uncompress_chunks(const uint8_t* d_in, const snb_chunk* h_chunks, si
   CK(g.outlen.ensure(count * 4));
   CK(cudaMemcpyAsync(g.chunks.p, h_chunks, count * sizeof(snb_chunk), cudaMemcpyHostToDevice, st));
   CKS(launch_decompress(d_in, d_out, g.chunks.as<snb::Chunk>(), (uint32_t)count, check_integrity,
-                        g.status.as<int32_t>(), g.outlen.as<uint32_t>(), st));
+                        g.status.as<int32_t>(), g.outlen.as<uint32_t>(), st, true));
   CK(cudaMemcpyAsync(h_status, g.status.p, count * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   prof_collect(8, 1, 4);
@@ -1565,7 +1575,7 @@ int snb_dev_uncompress_framed(const uint8_t* d_stream, uint64_t n, uint8_t* d_ou
     CK(g.status.ensure(count * 4));
     CK(g.outlen.ensure(count * 4));
     CKS(launch_decompress(d_stream, d_out, r.d_chunks, (uint32_t)count, check_integrity, g.status.as<int32_t>(),
-                          g.outlen.as<uint32_t>(), st));
+                          g.outlen.as<uint32_t>(), st, true));
     CK(cudaMemcpyAsync(status.data(), g.status.p, count * 4, cudaMemcpyDeviceToHost, st));
     tick("decode launched");
     CK(cudaStreamSynchronize(st));

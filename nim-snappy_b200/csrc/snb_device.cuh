@@ -1304,7 +1304,25 @@ struct DecompressArgs {
   uint32_t* counter;
   uint32_t count;
   uint32_t verify;     // 1: compare masked CRC of the produced bytes with chunk.crc
+  const uint32_t* order;   // optional: job j decodes chunk order[j] (largest compressed chunks first, decode_order_kernel)
 };
+
+// Longest job first: a chunk's decode time goes with its number of tags, i.e. with its compressed size, and a launch of
+// 16 384 chunks on 5 328 resident warps is three rounds and a fourth that is 7 % full -- the chunks that start last
+// should be the cheap ones.  Counting sort of the chunk indices by in_len / 256, descending; one CTA.
+__global__ void __launch_bounds__(1024) decode_order_kernel(const Chunk* chunks, uint32_t count, uint32_t* order) {
+  __shared__ uint32_t hist[260];
+  for (uint32_t i = threadIdx.x; i < 260; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) atomicAdd(&hist[257u - umin32(chunks[i].in_len >> 8, 257u)], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < 258; k++) { const uint32_t c = hist[k]; hist[k] = run; run += c; }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) order[atomicAdd(&hist[257u - umin32(chunks[i].in_len >> 8, 257u)], 1u)] = i;
+}
 
 // 6 warps x 6 CTAs = 36 warps per SM at 56 registers (no spills); measured on B200 (1 GiB text / mixed):
 // 256x4 154 / 214 GB/s, 128x9 154 / 221, 192x6 157 / 226, 128x10 148 / 216 (spills), 256x5 155 / 218 (spills)
@@ -1326,6 +1344,7 @@ __global__ void __launch_bounds__(SNB_DEC_THREADS, SNB_DEC_MINB) decompress_kern
     if (lane == 0) job = atomicAdd(a.counter, 1u);
     job = __shfl_sync(kFull, job, 0);
     if (job >= a.count) return;
+    if (a.order) job = a.order[job];
     Chunk c = a.chunks[job];
     const uint8_t* in = a.in_base + c.in_off;
     uint8_t* out = a.out_base + c.out_off;
