@@ -1568,6 +1568,7 @@ __global__ void __launch_bounds__(32) raw_validate_kernel(RawWalkArgs a) {
   const uint32_t lane = threadIdx.x;
   uint32_t X = a.br;   // the next true tag position
   bool dead = false;
+  uint32_t st_n = 0, st_ns = 0, st_long = 0;
   for (uint32_t s0 = 0; s0 < a.nseg; s0 += 32) {
     const uint32_t sj = s0 + lane;
     const uint32_t e2 = sj < a.nseg ? a.exit2[sj] : kWalkNone;
@@ -1593,11 +1594,28 @@ __global__ void __launch_bounds__(32) raw_validate_kernel(RawWalkArgs a) {
       const uint32_t aj = __shfl_sync(kFull, as, (int)j);
       if (aj != X) {   // entered somewhere else than assumed (after a jump)
         const unsigned long long t0 = snb_now_ns();
-        ej = raw_walk_warp<3>(a, s, X, lut, lane);
-        if (lane == 0) {   // statistics: re-walks, their time, the long ones
+        // The usual reason is a run of stored blocks: the chain lands on the tag of the next 64 KiB literal, which
+        // leaves this segment again.  One (uniform) look at that tag settles it -- same rules as raw_walk_warp
+        // (decoder.nim:54-75) -- without the 32-lane walk; everything else takes the walk.
+        uint32_t fast = kWalkNone;
+        {
+          const uint32_t avail = a.n - X;   // X < seg_hi <= n
+          // tag and the four bytes after it, requested together (one round trip); bytes past the stream read as 0
+          const uint32_t t = __ldg(a.in + X);
+          const uint32_t b1 = avail > 1 ? __ldg(a.in + X + 1) : 0u, b2 = avail > 2 ? __ldg(a.in + X + 2) : 0u;
+          const uint32_t b3 = avail > 3 ? __ldg(a.in + X + 3) : 0u, b4 = avail > 4 ? __ldg(a.in + X + 4) : 0u;
+          if ((t & 3u) == 0 && (t >> 2) >= 60 && avail - 1 >= 61) {
+            const uint32_t ll = (t >> 2) - 59;
+            const uint32_t v4 = b1 | (b2 << 8) | (b3 << 16) | (b4 << 24);
+            const uint32_t L = (ll == 4 ? v4 : (v4 & ((1u << (8 * ll)) - 1u))) + 1;
+            if (L != 0 && avail - (1 + ll) >= L && X + 1 + ll + L >= seg_hi) fast = X + 1 + ll + L;
+          }
+        }
+        ej = fast != kWalkNone ? fast : raw_walk_warp<3>(a, s, X, lut, lane);
+        {   // statistics (registers; written once at the end): re-walks, their time, the long ones
           const uint32_t dt = (uint32_t)(snb_now_ns() - t0);
-          a.flags[1]++; a.flags[2] += dt;
-          if (dt > 100000u) a.flags[3]++;
+          st_n++; st_ns += dt;
+          if (dt > 100000u) st_long++;
         }
       }
       if (lane == j) my_entry = X;
@@ -1606,6 +1624,7 @@ __global__ void __launch_bounds__(32) raw_validate_kernel(RawWalkArgs a) {
     }
     if (sj < a.nseg) a.entry[sj] = my_entry;
   }
+  if (lane == 0) { a.flags[1] = st_n; a.flags[2] = st_ns; a.flags[3] = st_long; }
   if (lane == 0 && (dead || X != a.n)) atomicOr(a.flags, 1u);
 }
 
