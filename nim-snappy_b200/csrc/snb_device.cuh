@@ -101,6 +101,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #ifndef SNB_V5_WDEPTH2
 #define SNB_V5_WDEPTH2 0   // 1: own words prefetched two windows ahead, so the hint never reads a load in flight (measured: 45.1 -> 44.4 GB/s)
 #endif
+#ifndef SNB_DEC_WINDOW
+#define SNB_DEC_WINDOW 0   // decoder: 1 = 256 stream bytes in a register window, read through shuffles (the round-1 formulation)
+#endif
 #ifndef SNB_V5_HINT
 #define SNB_V5_HINT 1   // 0: none, 1: L1 hint, 2: L2 hint for the next window's candidates
 #endif
@@ -1153,9 +1156,11 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
   // (Wc) is already on its way: the shuffles below read Wa and Wb in every step, so a row that has only just been
   // requested when the window slides would stall the warp for a DRAM round trip every 128 stream bytes
   // (25 % of the stall samples in profiles/r2_decompress_kernel_1GiB.txt)
+#if SNB_DEC_WINDOW
   uint32_t kb = 0;
   uint32_t Wa = __ldg(tw + umin32(lane, tw_last)), Wb = __ldg(tw + umin32(32 + lane, tw_last));
   uint32_t Wc = __ldg(tw + umin32(64 + lane, tw_last));
+#endif
   // short elements (<= 16 bytes) of the previous step: sources already loaded, stores still to do.  They are
   // flushed after the next step's tag parse, so the source loads never stall the warp.
   uint32_t pL = 0, pdst = 0, pssh = 0, px0 = 0, px1 = 0, px2 = 0, px3 = 0, px4 = 0;
@@ -1177,6 +1182,7 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
   } while (0)
 
   while (ip < tn) {
+#if SNB_DEC_WINDOW
     // ---- the 36 stream bytes of this step, assembled from the register window through shuffles
     const uint32_t i0 = ip + tmis;
     {
@@ -1195,6 +1201,12 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
       const uint32_t a2 = __shfl_sync(kFull, Wa, (int)j + 2), b2 = __shfl_sync(kFull, Wb, (int)j + 2);
       w0 = j < 32 ? a0 : b0; w1 = j + 1 < 32 ? a1 : b1; w2 = j + 2 < 32 ? a2 : b2;
     }
+#else
+    // ---- the 36 stream bytes of this step straight from the L1 (three word loads per lane, 44 contiguous bytes per
+    // warp): 7 instructions instead of the 17 of the register window, and 36 warps per SM cover the L1 latency
+    const uint32_t i1 = ip + tmis + lane, k1 = i1 >> 2, sh = (i1 & 3) * 8;
+    const uint32_t w0 = __ldg(tw + umin32(k1, tw_last)), w1 = __ldg(tw + umin32(k1 + 1, tw_last)), w2 = __ldg(tw + umin32(k1 + 2, tw_last));
+#endif
     const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
     const uint32_t pos = ip + lane;
     const bool inb = pos < tn;
