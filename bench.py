@@ -331,19 +331,26 @@ def _peak():
 def bench_mixed(args, dc, lib, max_over_ranks, barrier, world, rank, d_in, d_out, d_back):
     """BASELINE configs[4]: 64 GiB of the mixed corpus (text | protobuf-like | random per MiB) sharded over the ranks
     (strong scaling: 64 / N GiB per GPU), framed compress + uncompress, device resident.  A rank's share is processed as
-    passes over a 1 GiB device block (the headline's buffers are reused; a different 3 MiB phase per pass would not
-    change a byte of any chunk's encoding: chunks are independent)."""
+    passes over a device block of up to 4 GiB (1 GiB of corpus generated on the host, repeated on the device: chunks are
+    independent, so a different phase per GiB would not change a byte of any chunk's encoding)."""
     import torch
     from nim_snappy_b200.workloads import mixed_corpus
     from oracle import oracle as o
-    n = d_in.numel()
+    n1 = d_in.numel()
     total = args.mixed_gib << 30
-    passes = max(1, total // world // n)
-    h = mixed_corpus(n, seed=rank, phase_mib=rank)
+    share = max(n1, total // world)
+    reps = max(1, min(4, share // n1))                 # device block: up to 4 x the headline's size (4 GiB)
+    n = n1 * reps
+    passes = max(1, share // n)
+    h = mixed_corpus(n1, seed=rank, phase_mib=rank)
     d_in.copy_(torch.from_numpy(h))
+    if reps > 1:
+        d_in = d_in.repeat(reps)
+        d_out = torch.empty(int(lib.snb_max_compressed_len_framed(n)), dtype=torch.uint8, device="cuda")
+        d_back = torch.empty(n, dtype=torch.uint8, device="cuda")
     lens = torch.zeros(n // CHUNK, dtype=torch.int32, device="cuda")
     _, w = dc.compress_framed(d_in, out=d_out, with_header=True, frame_lens=lens)
-    sample = min(n, 48 << 20)
+    sample = min(n1, 48 << 20)
     exp = o.compress_framed(h[:sample], as_array=True)[1]
     ok = bool(np.array_equal(d_out[:exp.size].cpu().numpy(), exp))
     barrier()
@@ -358,6 +365,7 @@ def bench_mixed(args, dc, lib, max_over_ranks, barrier, world, rank, d_in, d_out
     return {"workload": f"{args.mixed_gib} GiB mixed corpus (1 MiB text | 1 MiB protobuf-like | 1 MiB random) sharded over {world} GPU(s), "
                         f"framed compress + uncompress, device resident, BASELINE configs[4]",
             "scaling": "strong", "bytes_total": int(done), "bytes_per_gpu": int(passes * n), "passes_per_gpu": int(passes),
+            "bytes_per_pass": int(n),
             "compressed_fraction": round(w / n, 4),
             "value": round(done / c_ms / 1e6, 3), "unit": UNIT, "ms_total": round(c_ms, 3),
             "roofline_frac_per_gpu": round((n + w) * passes / c_ms / 1e6 / peak, 5),

@@ -34,7 +34,11 @@ namespace {
 constexpr uint64_t kChunk = snb::kMaxBlock;
 constexpr uint64_t kFrameStride = 65664;           // >= 65544 (stored frame) and >= the abort bound, multiple of 128
 constexpr uint64_t kRawStride = 76544;             // >= maxCompressedLen(65536) = 76490, multiple of 128
-constexpr uint32_t kDevSlabChunks = 16384;         // 1 GiB of input per device-side slab
+constexpr uint32_t kDevSlabChunks = 16384;         // 1 GiB of input per slab of the host-buffer pipeline
+// Device-resident input: up to 4 GiB per launch.  A launch ends with idle warps (16 384 chunks are 5.03 per encoder
+// warp), which costs 4-5 % at 1 GiB and a quarter of that at 4 GiB (45.4 -> 47.5 GB/s on the text corpus); the scratch
+// slots of a slab are 4.3 GB.
+constexpr uint32_t kDevStreamSlabChunks = 65536;
 constexpr uint32_t kHostSlabChunks = 4096;         // 256 MiB of input per host<->device slab (fills 148 SMs x 20 encoder warps)
 constexpr uint32_t kGroupShift = 9;                // streaming pipeline: 512 chunks (32 MiB of input) per H2D piece / D2H group
 constexpr uint32_t kGroupChunks = 1u << kGroupShift;
@@ -374,7 +378,7 @@ int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
     CK(cudaMemcpyAsync(g.d_total, &dst_base, 8, cudaMemcpyHostToDevice, st));
     return SNB_OK;
   }
-  const uint32_t slab = (uint32_t)std::min<uint64_t>(count64, kDevSlabChunks);
+  const uint32_t slab = (uint32_t)std::min<uint64_t>(count64, kDevStreamSlabChunks);
   const uint64_t kSlotStride = mode == snb::kModeFrame ? kFrameStride : kRawStride;
   CompressGeom cg = compress_geom((uint32_t)kChunk, slab);
   // the CRC tables share the dynamic shared memory with the hash tables
