@@ -202,9 +202,13 @@ void snb_set_compress_warps(int warps);
 /* A-B testing of the block encoder for 64 KiB chunks: 0 / 5 = one warp per chunk (default), 6 = resolver warps + walker
  * warp per chunk with every hash table in shared memory (experimental: byte-identical, slower). */
 void snb_set_compress_algo(int algo);
-/* How long the streaming compress kernel waits for a chunk whose host-to-device copy has not landed (default 2000 ms;
- * then the call returns SNB_TIMEOUT instead of hanging). */
+/* How long the streaming compress kernel waits for a chunk whose host-to-device copy has not landed (default 2000 ms).
+ * A host-buffer call whose kernel gave up is repeated once with every copy enqueued ahead of its kernel (pageable input
+ * is normally copied while the kernel already runs; another thread's cudaMalloc / cudaFree can hold that up); only if
+ * the repeat times out too does the call return SNB_TIMEOUT instead of hanging. */
 void snb_set_arrive_timeout_ms(int ms);
+/* Host-buffer compress calls that timed out once and were repeated (see above) -- for tests. */
+uint64_t snb_timeouts_recovered(void);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,7 @@ SIGNATURES = {
     "snb_kernel_launches": (_u64, []),
     "snb_raw_block_decodes": (_u64, []),
     "snb_frame_index_fallbacks": (_u64, []),
+    "snb_timeouts_recovered": (_u64, []),
     "snb_debug_kernel_span_ns": (_u64, []),
     "snb_set_compress_warps": (None, [_i]),
     "snb_set_compress_algo": (None, [_i]),

@@ -117,6 +117,7 @@ struct Ctx {
                                                   // (47 vs 23.7 ms; profiles/r2_ncu_bisect.log), i.e. every capture described a different kernel.
   float l2_ratio = 0.f;                           // 0: derive from the carve-out and the table bytes
   uint32_t dec_slab_chunks = 1024;  // host decode pipeline: chunks per H2D | kernel | D2H slab (64 MiB of output: short fill / drain)
+  uint64_t timeouts_recovered = 0;  // streaming compress attempts that timed out and were repeated copies-first
   int arrive_timeout_ms = 2000;     // streaming compress: a chunk whose input has not landed after this long ends the call with SNB_TIMEOUT
   std::string err;
 };
@@ -505,7 +506,7 @@ int wait_group_flag(volatile unsigned long long* flag, cudaEvent_t kernel_done, 
   }
 }
 
-int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, uint32_t mode) {
+int host_compress_once(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, uint32_t mode, bool force_copies_first) {
   if (n == 0) return SNB_OK;
   const bool dbg_e2e = getenv("SNB_DEBUG_E2E") != nullptr;   // host-side timeline of the streaming pipeline on stderr
   const auto t_begin = std::chrono::steady_clock::now();
@@ -576,7 +577,10 @@ int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, ui
     // them.  Pageable input: cudaMemcpyAsync blocks the host while it stages, so the kernel goes first and waits for
     // its pieces -- unless launches block (profilers serialise them): a kernel launched before its copies would then
     // spin until its timeout.
-    const bool copies_first = pinned_in || g.blocking_launches;
+    // Small pageable inputs (staged in a few ms) and the retry after a timeout also go copies-first: a kernel that
+    // waits for copies which are not enqueued yet depends on this host thread getting through the driver, and another
+    // thread's cudaMalloc / cudaFree (which waits for the spinning kernel while holding driver locks) can stop it.
+    const bool copies_first = pinned_in || g.blocking_launches || force_copies_first || n <= (64ull << 20);
 #endif
     if (copies_first) { CKS(copy_in(k)); CKS(launch(k)); }
     else { CKS(launch(k)); CKS(copy_in(k)); }
@@ -612,6 +616,19 @@ int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, ui
   if (dbg_e2e) fprintf(stderr, "host_compress: all streams drained at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
   if (*g.h_meta[0].as<uint32_t>() != 0) { g.err = "streaming compress: timed out waiting for input pieces (a host-to-device copy did not arrive)"; return SNB_TIMEOUT; }
   return SNB_OK;
+}
+
+// A timed-out attempt (the kernel gave up on a piece this thread had not managed to enqueue) is repeated once with every
+// copy of a slab enqueued before its kernel: copies that sit in the hardware queue need nothing more from the host.
+int host_compress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t* pos, uint32_t mode) {
+  const uint64_t pos0 = *pos;
+  int st = host_compress_once(in, n, out, pos, mode, false);
+  if (st == SNB_TIMEOUT) {
+    g.timeouts_recovered++;
+    *pos = pos0;
+    st = host_compress_once(in, n, out, pos, mode, true);
+  }
+  return st;
 }
 
 // ---------------------------------------------------------------- framed header walk (snappy.nim:186-267)
@@ -990,7 +1007,8 @@ int dev_frame_index(const uint8_t* d_stream, uint64_t n, uint64_t out_cap, int c
     SNB_LAUNCH(link_kernel, cg, 256, 0, st, a, (uint32_t)n_cand); count_launch();
     uint32_t rounds = 1;
     while ((1ull << rounds) < n_cand + 1) rounds++;
-    for (uint32_t k = 0; k <= rounds; k++) { SNB_LAUNCH(reach_kernel, cg, 256, 0, st, a, (uint32_t)n_cand, k & 1u); count_launch(); }
+    if (n_cand <= (1u << 17)) { SNB_LAUNCH(reach_fused_kernel, 1, 1024, 0, st, a, (uint32_t)n_cand, rounds); count_launch(); }
+    else for (uint32_t k = 0; k <= rounds; k++) { SNB_LAUNCH(reach_kernel, cg, 256, 0, st, a, (uint32_t)n_cand, k & 1u); count_launch(); }
     SNB_LAUNCH(chain_count_kernel, cg, 256, 0, st, a, (uint32_t)n_cand); count_launch();
     SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, st, a.blk_count, (uint64_t*)a.blk_off, cg, (const uint64_t*)nullptr, 0ull, (uint64_t*)d_tot);
     count_launch();
@@ -1717,6 +1735,7 @@ int snb_get_profile(float* ms, int n) {
 uint64_t snb_kernel_launches(void) { return g.launches; }
 uint64_t snb_raw_block_decodes(void) { return g.raw_block_decodes; }
 uint64_t snb_frame_index_fallbacks(void) { return g.index_fallbacks; }
+uint64_t snb_timeouts_recovered(void) { return g.timeouts_recovered; }
 // Debug (SNB_DEBUG_SPAN=1): nanoseconds between the first CTA's start and the last warp's exit of the last streaming
 // compress kernel, read from %globaltimer inside the kernel; synchronises the device.  0 when not enabled.
 uint64_t snb_debug_kernel_span_ns(void) {

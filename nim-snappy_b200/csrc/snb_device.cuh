@@ -104,6 +104,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #ifndef SNB_DEC_WINDOW
 #define SNB_DEC_WINDOW 0   // decoder: 1 = 256 stream bytes in a register window, read through shuffles (the round-1 formulation)
 #endif
+#ifndef SNB_V5_SKIP_PASSED
+#define SNB_V5_SKIP_PASSED 0   // 1 / 2 / 3: no table / candidate loads for the lanes behind the cursor (an eighth of a pass's random
+                               // sectors).  Byte-exact and measured SLOWER, reproducibly: 23.74 ms -> 25.05 (branch), 24.77 (branch-free,
+                               // the skipped lanes read hot addresses), 25.2 (the ip-1 lane still reads its slot) per 1 GiB of text
+#endif
 #ifndef SNB_V5_HINT
 #define SNB_V5_HINT 1   // 0: none, 1: L1 hint, 2: L2 hint for the next window's candidates
 #endif
@@ -507,20 +512,40 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     const uint32_t w2 = __shfl_sync(kFull, W, (int)own_q + 2), w3 = __shfl_sync(kFull, W, (int)own_q + 3);
     const uint32_t a0 = __funnelshift_r(w0, w1, own_s), a1 = __funnelshift_r(w1, w2, own_s), a2 = __funnelshift_r(w2, w3, own_s);
     const uint32_t h = hash14(a0, mask);
-    const uint32_t T = table[h];
+#if SNB_V5_SKIP_PASSED
+    // lanes before the pass's entry position are behind the cursor: they are never looked up in this pass (they only
+    // lend their hash to the insert of ip-1 and to the group masks), so their table entry and candidate bytes are not
+    // fetched -- an eighth of a pass's random sectors on text (the entry sits 4 lanes into the window on average)
+    const uint32_t c_in = (chain ? ip : pp) - b;
+    const bool need = lane >= c_in;
+    // the lane just before the entry is inserted by this pass (ip-1): it still reads its slot, so that the commit's
+    // 16-bit store lands in a sector the L2 holds completely (a partial-sector write miss is a DRAM read-modify-write)
+    const bool need_t = SNB_V5_SKIP_PASSED == 3 ? lane + 1 >= c_in : need;
+#else
+    const bool need = true, need_t = true;
+#endif
+#if SNB_V5_SKIP_PASSED == 2
+    // branch-free form: the skipped lanes read slot 0 and the window's own first bytes (both hot), and report no match
+    const uint32_t T = need ? table[h] : table[0];
+    const uint32_t Tc = need ? T : b;
+#else
+    const uint32_t T = need_t ? table[h] : 0u;
+    const uint32_t Tc = T;
+#endif
     SNB_CYC_MARK(0, T);
-    uint32_t ml;
-    {
+    uint32_t ml = 0;
+    if (SNB_V5_SKIP_PASSED == 2 || need) {
       uint32_t c0, c1, c2;
 #if SNB_V5_CAND128
-      in_ld12a(v, T, c0, c1, c2);
+      in_ld12a(v, Tc, c0, c1, c2);
 #else
-      in_ld12u(v, T, c0, c1, c2);
+      in_ld12u(v, Tc, c0, c1, c2);
 #endif
       const uint32_t x0 = a0 ^ c0, x1 = a1 ^ c1, x2 = a2 ^ c2;
       const uint32_t xs = x0 ? x0 : (x1 ? x1 : x2);
       const uint32_t base = x0 ? 0u : (x1 ? 4u : 8u);
       ml = xs ? base + first_diff_byte(xs) : 12u;
+      if (!need) ml = 0;
     }
     SNB_CYC_MARK(1, ml);
     const uint32_t off = p - T;
@@ -1049,37 +1074,43 @@ __global__ void __launch_bounds__(256) crc_kernel(CrcArgs a, const CrcTables* g)
 
 // ===================================================================== scan + compaction
 // Exclusive prefix sum of lens[0..count) into offs (u64), starting at base_const + *base_ptr;
-// end offset into *total (may alias base_ptr).  One CTA.
+// end offset into *total (may alias base_ptr).  One CTA: every thread sums a contiguous run of ceil(count / threads)
+// elements, one block-wide scan of the per-thread sums, then the run is written -- three barriers whatever the count
+// (the tile-by-tile form this replaces took 1.5 us per 1 024 elements: 29 us for the 17 759 block counts of a frame
+// index, 1.4 ms for a batch of a million messages).
 __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* lens, uint64_t* offs, uint32_t count,
                                                     const uint64_t* base_ptr, uint64_t base_const, uint64_t* total) {
   __shared__ unsigned long long warp_sums[32];
-  __shared__ unsigned long long carry_s;
-  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if (threadIdx.x == 0) carry_s = base_const + (base_ptr ? *base_ptr : 0ull);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const uint32_t per = (count + blockDim.x - 1) / blockDim.x;
+  const uint64_t lo64 = (uint64_t)threadIdx.x * per;
+  const uint32_t lo = lo64 < count ? (uint32_t)lo64 : count;
+  const uint32_t hi = count - lo < per ? count : lo + per;
+  unsigned long long sum = 0;
+  for (uint32_t i = lo; i < hi; i++) sum += lens[i];
+  unsigned long long incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned long long u = __shfl_up_sync(kFull, incl, d);
+    if (lane >= (uint32_t)d) incl += u;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
   __syncthreads();
-  for (uint32_t start = 0; start < count; start += blockDim.x) {
-    uint32_t i = start + threadIdx.x;
-    unsigned long long v = i < count ? lens[i] : 0, incl = v;
+  if (warp == 0) {   // inclusive scan of the warp totals
+    unsigned long long w = lane < nw ? warp_sums[lane] : 0ull;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      unsigned long long u = __shfl_up_sync(kFull, incl, d);
-      if (lane >= (uint32_t)d) incl += u;
+      unsigned long long u = __shfl_up_sync(kFull, w, d);
+      if (lane >= (uint32_t)d) w += u;
     }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    unsigned long long wprefix = 0;
-    for (uint32_t w = 0; w < warp; w++) wprefix += warp_sums[w];
-    unsigned long long carry = carry_s;
-    if (i < count) offs[i] = carry + wprefix + incl - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) {
-      unsigned long long t = 0;
-      for (uint32_t w = 0; w < nw; w++) t += warp_sums[w];
-      carry_s = carry + t;
-    }
-    __syncthreads();
+    warp_sums[lane] = w;
   }
-  if (threadIdx.x == 0) *total = carry_s;
+  __syncthreads();
+  const unsigned long long base = base_const + (base_ptr ? *base_ptr : 0ull);
+  unsigned long long run = base + (warp ? warp_sums[warp - 1] : 0ull) + incl - sum;
+  __syncthreads();   // every thread has read *base_ptr before thread 0 may overwrite it through `total`
+  for (uint32_t i = lo; i < hi; i++) { const unsigned long long v = lens[i]; offs[i] = run; run += v; }
+  if (threadIdx.x == blockDim.x - 1) *total = base + warp_sums[31 < nw ? 31 : nw - 1];
 }
 
 // ===================================================================== decompress

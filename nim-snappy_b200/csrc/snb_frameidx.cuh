@@ -24,12 +24,18 @@
 namespace snb {
 namespace fidx {
 
-constexpr uint32_t kScanThreads = 1024;         // 8 words per thread and CTA: the scan is bound by DRAM latency, so many warps and a prefetch
+#ifndef SNB_FIDX_THREADS
+#define SNB_FIDX_THREADS 256
+#endif
+#ifndef SNB_FIDX_HOPS
+#define SNB_FIDX_HOPS 3
+#endif
+constexpr uint32_t kScanThreads = SNB_FIDX_THREADS;         // 8 CTAs per SM: while one CTA waits for its stage-2 hops the others scan (1 024 threads: 0.73 ms per index, 512: 0.56, 256: 0.53, 128: 0.55)
 constexpr uint32_t kScanBytes = 32768;          // stream bytes per CTA
 constexpr uint32_t kBlockCands = 1024;          // candidate slots per CTA (after the successor checks: a handful per 32 KiB)
 constexpr uint32_t kStage1 = 8192;              // positions per CTA that pass the register-only test (text: ~200 of 32 768)
 constexpr uint32_t SNB_MAX_FRAME_DATA = 76490u + 4u;   // codec.nim:216-219 + the CRC
-constexpr uint32_t kHops = 3;                   // successors a candidate must lead to (or the end of the stream)
+constexpr uint32_t kHops = SNB_FIDX_HOPS;                   // successors a candidate must lead to (or the end of the stream)
 constexpr uint32_t kEnd = 0xfffffffeu, kDead = 0xffffffffu;
 constexpr uint32_t kMaxSkippable = 1u << 16;    // longest skippable chunk the candidate scan considers
 
@@ -261,6 +267,27 @@ __global__ void __launch_bounds__(256) reach_kernel(Args a, uint32_t n_cand, uin
     nxt[i] = j;
     if (j == kEnd && a.mark[i]) a.sum->reached_end = 1u;   // (only the last chain node ever keeps kEnd as its 1-step target
   }                                                         //  through all rounds; earlier ones reach it by jumping)
+}
+
+// All the doubling rounds in one launch when one CTA can sweep the candidates quickly (a 582 MB text stream has 16 600:
+// seventeen launches of 3.6 us each become one of ~15 us).  The barrier between rounds is all the ordering the rounds
+// need: a node marked during round k only has to act from round k + 1 on.
+__global__ void __launch_bounds__(1024) reach_fused_kernel(Args a, uint32_t n_cand, uint32_t rounds) {
+  for (uint32_t k = 0; k <= rounds; k++) {
+    const uint32_t* cur = a.nxt[k & 1u];
+    uint32_t* nxt = a.nxt[(k & 1u) ^ 1u];
+    for (uint32_t i = threadIdx.x; i < n_cand; i += blockDim.x) {
+      const uint32_t j = cur[i];
+      if (j < n_cand) {
+        if (a.mark[i]) a.mark[j] = 1u;
+        nxt[i] = cur[j];
+      } else {
+        nxt[i] = j;
+        if (j == kEnd && a.mark[i]) a.sum->reached_end = 1u;
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // chain: reached candidates in order (they are sorted by position, and the walk only moves forward).

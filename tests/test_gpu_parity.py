@@ -443,3 +443,35 @@ def test_concurrent_callers_and_streams(gpu_api, dc, oracle):
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+def test_streaming_compress_survives_allocator_traffic(gpu_api, oracle):
+    """A pageable input above 64 MiB is copied while the streaming kernel already runs; cudaMalloc / cudaFree from another
+    thread waits for that kernel and can keep the copying thread out of the driver.  The kernel then gives up after its
+    timeout and the call is repeated with the copies enqueued first: the result is byte-exact either way, never
+    SNB_TIMEOUT (include/snb.h, snb_set_arrive_timeout_ms)."""
+    import threading
+    import torch
+    from nim_snappy_b200.workloads import text_corpus
+    data = text_corpus(96 << 20, phase=77).tobytes()
+    expect = oracle.encode_framed(data)
+    lib = gpu_api.lib
+    stop = threading.Event()
+
+    def churn():
+        while not stop.is_set():
+            t = torch.empty(48 << 20, dtype=torch.uint8, device="cuda")
+            del t
+            torch.cuda.empty_cache()      # cudaFree: device-wide synchronisation point
+
+    lib.snb_set_arrive_timeout_ms(300)    # keep a recovered attempt short
+    th = threading.Thread(target=churn)
+    th.start()
+    try:
+        for _ in range(6):
+            assert gpu_api.encodeFramed(data) == expect
+    finally:
+        stop.set()
+        th.join()
+        lib.snb_set_arrive_timeout_ms(2000)
+    print("timeouts recovered:", lib.snb_timeouts_recovered())
