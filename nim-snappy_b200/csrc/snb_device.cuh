@@ -109,6 +109,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
                                // sectors).  Byte-exact and measured SLOWER, reproducibly: 23.74 ms -> 25.05 (branch), 24.77 (branch-free,
                                // the skipped lanes read hot addresses), 25.2 (the ip-1 lane still reads its slot) per 1 GiB of text
 #endif
+#ifndef SNB_V5_HINT_AHEAD2
+#define SNB_V5_HINT_AHEAD2 0
+#endif
 #ifndef SNB_V5_HINT
 #define SNB_V5_HINT 1   // 0: none, 1: L1 hint, 2: L2 hint for the next window's candidates
 #endif
@@ -569,7 +572,11 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
     // hint for the next window: its (pre-commit) table entries say where its candidates most likely are
     uint32_t Tn;
     {
+#if SNB_V5_HINT_AHEAD2   // (needs SNB_V5_WDEPTH2) hint two windows ahead: a whole pass for the table sector and the candidate line to arrive
+      const uint32_t n0 = __shfl_sync(kFull, Wm, (int)own_q), n1 = __shfl_sync(kFull, Wm, (int)own_q + 1);
+#else
       const uint32_t n0 = __shfl_sync(kFull, Wn, (int)own_q), n1 = __shfl_sync(kFull, Wn, (int)own_q + 1);
+#endif
       Tn = table[hash14(__funnelshift_r(n0, n1, own_s), mask)];
     }
     SNB_CYC_MARK(3, Tn);
