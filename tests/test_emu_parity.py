@@ -125,6 +125,15 @@ def test_host_message_batch(emu_api, oracle):
     P.check_batch(emu_api, oracle, msgs, extra_streams=V.MALFORMED_RAW[:8] + [b"\x05", b""])
 
 
+def test_host_message_batch_many(emu_api, oracle):
+    """More messages than the single-CTA prefix sum has threads (every thread then owns a run of lengths): the packed
+    output offsets of snb_compress_batch must still be the running sum."""
+    rng = np.random.default_rng(19)
+    src = read_data("alice29.txt")
+    msgs = [src[o:o + n] for o, n in zip(rng.integers(0, len(src) - 64, 2500), rng.integers(0, 48, 2500))]
+    P.check_batch(emu_api, oracle, msgs)
+
+
 def test_device_side_header_walk(emu_api, oracle):
     """snb_dev_uncompress_framed: the header walk of snappy.nim:199-265 done on the device (candidate scan, links,
     pointer jumping) must give the reference's statuses, (read, written) and bytes -- valid streams, every partial-output
