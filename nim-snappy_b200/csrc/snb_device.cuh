@@ -109,6 +109,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
                                // sectors).  Byte-exact and measured SLOWER, reproducibly: 23.74 ms -> 25.05 (branch), 24.77 (branch-free,
                                // the skipped lanes read hot addresses), 25.2 (the ip-1 lane still reads its slot) per 1 GiB of text
 #endif
+#ifndef SNB_V5_LANDING
+#define SNB_V5_LANDING 0   // 1: the landing window's own words are requested as soon as a long match ends (measured neutral: 23.78 -> 23.84 ms)
+#endif
 #ifndef SNB_V5_HINT_AHEAD2
 #define SNB_V5_HINT_AHEAD2 0
 #endif
@@ -680,7 +683,14 @@ __device__ __forceinline__ uint32_t compress_block_v5(const uint8_t* __restrict_
       if (op > abort_thr) return kAborted;
       if (ip > ip_limit) { done = true; break; }
       c = ip - b;
-      if (c >= 32) break;
+      if (c >= 32) {
+#if SNB_V5_LANDING
+        // a long match lands beyond the window whose words are already here: ask for the landing window's now, the
+        // copy tag and the commit below run while they travel (565 of a text chunk's 2 090 passes start this way)
+        if (c >= 64) { Wn_b = ip & ~31u; Wn = __ldg(v.w + umin32((Wn_b >> 2) + wlane, v.last)); }
+#endif
+        break;
+      }
     }
     if (chain && !force_slow && ip > ip_limit) done = true;   // encoder.nim:362-363
     // the next arrival's ip-1 insert when no window pass will own it (lane c-1 of the arrival rule)
