@@ -101,6 +101,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #ifndef SNB_V5_WDEPTH2
 #define SNB_V5_WDEPTH2 0   // 1: own words prefetched two windows ahead, so the hint never reads a load in flight (measured: 45.1 -> 44.4 GB/s)
 #endif
+#ifndef SNB_DEC_PREFETCH
+#define SNB_DEC_PREFETCH 256   // bytes ahead of the step that the stream is prefetched into the L1 (0: off -- 6.19 ms per 1 GiB text; 128: 6.04, 256: 6.03, 512: 6.05)
+#endif
 #ifndef SNB_DEC_WINDOW
 #define SNB_DEC_WINDOW 0   // decoder: 1 = 256 stream bytes in a register window, read through shuffles (the round-1 formulation)
 #endif
@@ -1390,9 +1393,6 @@ __global__ void __launch_bounds__(1024) decode_order_kernel(const Chunk* chunks,
 
 // 6 warps x 6 CTAs = 36 warps per SM at 56 registers (no spills); measured on B200 (1 GiB text / mixed):
 // 256x4 154 / 214 GB/s, 128x9 154 / 221, 192x6 157 / 226, 128x10 148 / 216 (spills), 256x5 155 / 218 (spills)
-#ifndef SNB_DEC_PREFETCH
-#define SNB_DEC_PREFETCH 256   // bytes ahead of the step that the stream is prefetched into the L1 (0: off -- 6.19 ms per 1 GiB text; 128: 6.04, 256: 6.03, 512: 6.05)
-#endif
 #ifndef SNB_DEC_MINB
 #define SNB_DEC_MINB 6
 #endif
