@@ -1107,6 +1107,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* lens, uint64
   const uint32_t lo = lo64 < count ? (uint32_t)lo64 : count;
   const uint32_t hi = count - lo < per ? count : lo + per;
   unsigned long long sum = 0;
+#pragma unroll 8
   for (uint32_t i = lo; i < hi; i++) sum += lens[i];
   unsigned long long incl = sum;
 #pragma unroll
@@ -1129,6 +1130,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* lens, uint64
   const unsigned long long base = base_const + (base_ptr ? *base_ptr : 0ull);
   unsigned long long run = base + (warp ? warp_sums[warp - 1] : 0ull) + incl - sum;
   __syncthreads();   // every thread has read *base_ptr before thread 0 may overwrite it through `total`
+#pragma unroll 8
   for (uint32_t i = lo; i < hi; i++) { const unsigned long long v = lens[i]; offs[i] = run; run += v; }
   if (threadIdx.x == blockDim.x - 1) *total = base + warp_sums[31 < nw ? 31 : nw - 1];
 }
