@@ -380,8 +380,13 @@ int dev_compress_stream(const uint8_t* d_in, uint64_t n, uint32_t mode, uint8_t*
     CK(cudaMemcpyAsync(g.d_total, &dst_base, 8, cudaMemcpyHostToDevice, st));
     return SNB_OK;
   }
-  const uint32_t slab = (uint32_t)std::min<uint64_t>(count64, kDevStreamSlabChunks);
+  uint32_t slab = (uint32_t)std::min<uint64_t>(count64, kDevStreamSlabChunks);
   const uint64_t kSlotStride = mode == snb::kModeFrame ? kFrameStride : kRawStride;
+  // the scratch slots of a 4 GiB launch are 4.3 GB: when the device cannot spare them, 1 GiB launches do
+  if (slab > kDevSlabChunks && g.scratch.ensure((size_t)slab * kSlotStride + 4096) != cudaSuccess) {
+    cudaGetLastError();
+    slab = kDevSlabChunks;
+  }
   CompressGeom cg = compress_geom((uint32_t)kChunk, slab);
   // the CRC tables share the dynamic shared memory with the hash tables
   while (cg.smem_warps > 0 && cg.smem_warps * (size_t)cg.entries * 2 + sizeof(snb::CrcSmem) > 227 * 1024) cg.smem_warps--;
