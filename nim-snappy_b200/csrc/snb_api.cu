@@ -267,7 +267,6 @@ int do_init(int device) {
 #endif
   CK(cudaFuncSetAttribute(snb::compress_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
   CK(cudaFuncSetAttribute(snb::compress_kernel5, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemMax));
-  CK(cudaFuncSetAttribute(snb::fidx::reach_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 18000 * 12));
 #ifndef SNB_EMULATE
   {  // do launches block?  (second launch: the first one pays for loading the module)
     SNB_LAUNCH(snb::launch_probe_kernel, 1, 1, 0, g.s0, 0u);
@@ -1013,11 +1012,7 @@ int dev_frame_index(const uint8_t* d_stream, uint64_t n, uint64_t out_cap, int c
     SNB_LAUNCH(link_kernel, cg, 256, 0, st, a, (uint32_t)n_cand); count_launch();
     uint32_t rounds = 1;
     while ((1ull << rounds) < n_cand + 1) rounds++;
-    if (n_cand <= (1u << 17)) {
-      const uint32_t in_smem = n_cand <= 18000 ? 1u : 0u;      // 12 bytes per candidate of the 227 KiB a CTA may have
-      const size_t sm = in_smem ? n_cand * 12 : 0;
-      SNB_LAUNCH(reach_fused_kernel, 1, 1024, sm, st, a, (uint32_t)n_cand, rounds, in_smem); count_launch();
-    }
+    if (n_cand <= (1u << 17)) { SNB_LAUNCH(reach_fused_kernel, 1, 1024, 0, st, a, (uint32_t)n_cand, rounds); count_launch(); }
     else for (uint32_t k = 0; k <= rounds; k++) { SNB_LAUNCH(reach_kernel, cg, 256, 0, st, a, (uint32_t)n_cand, k & 1u); count_launch(); }
     SNB_LAUNCH(chain_count_kernel, cg, 256, 0, st, a, (uint32_t)n_cand); count_launch();
     SNB_LAUNCH(snb::scan_kernel, 1, 1024, 0, st, a.blk_count, (uint64_t*)a.blk_off, cg, (const uint64_t*)nullptr, 0ull, (uint64_t*)d_tot);
