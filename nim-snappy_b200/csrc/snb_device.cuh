@@ -104,6 +104,15 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #ifndef SNB_DEC_PREFETCH
 #define SNB_DEC_PREFETCH 256   // bytes ahead of the step that the stream is prefetched into the L1 (0: off -- 6.19 ms per 1 GiB text; 128: 6.04, 256: 6.03, 512: 6.05)
 #endif
+#ifndef SNB_DEC_FASTFETCH
+#define SNB_DEC_FASTFETCH 1   // decoder: unclamped stream loads while the step is >= 320 bytes away from the end of the stream
+#endif
+#ifndef SNB_DEC_LUT32
+#define SNB_DEC_LUT32 1       // decoder: tag table read through a 32-bit shared address
+#endif
+#ifndef SNB_DEC_SHFLPRED
+#define SNB_DEC_SHFLPRED 1    // decoder: prefix sum rounds use shfl.up's range predicate
+#endif
 #ifndef SNB_DEC_WINDOW
 #define SNB_DEC_WINDOW 0   // decoder: 1 = 256 stream bytes in a register window, read through shuffles (the round-1 formulation)
 #endif
@@ -1174,6 +1183,10 @@ __device__ __forceinline__ void stage_tag_lut(uint2* lut) {
   __syncthreads();
 }
 
+// kOverRead: the caller guarantees that the kDecOverRead bytes after in[n) are readable (they belong to a later
+// chunk of the same buffer), so the stream loads need no clamping.
+constexpr uint32_t kDecOverRead = SNB_DEC_PREFETCH + 64;
+template <bool kOverRead>
 __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ in, uint32_t n, uint8_t* out,
                                                    uint32_t cap, uint32_t* written, uint32_t lane, const uint2* lut,
                                                    bool bare = false) {
@@ -1204,7 +1217,9 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
   // aligned word view of the tag stream: word 0 holds tags[0] at byte `tmis`
   const uint32_t tmis = (uint32_t)((uintptr_t)tags & 3);
   const uint32_t* const tw = (const uint32_t*)(tags - tmis);
+#if SNB_DEC_WINDOW
   const uint32_t tw_last = (tn + tmis - 1) >> 2;   // tn >= 1 here
+#endif
   // 256 stream bytes held in registers: lane l has words kb + l (Wa) and kb + 32 + l (Wb).  The row after them
   // (Wc) is already on its way: the shuffles below read Wa and Wb in every step, so a row that has only just been
   // requested when the window slides would stall the warp for a DRAM round trip every 128 stream bytes
@@ -1217,6 +1232,10 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
   // short elements (<= 16 bytes) of the previous step: sources already loaded, stores still to do.  They are
   // flushed after the next step's tag parse, so the source loads never stall the warp.
   uint32_t pL = 0, pdst = 0, pssh = 0, px0 = 0, px1 = 0, px2 = 0, px3 = 0, px4 = 0;
+#if SNB_DEC_LUT32 && !defined(SNB_EMULATE)
+  uint32_t lut_s;
+  asm volatile("mov.u32 %0, %1;" : "=r"(lut_s) : "r"((uint32_t)__cvta_generic_to_shared(lut)));   // opaque: not rematerialised in the loop
+#endif
 
 #define SNB_FLUSH_SHORT()                                                                         \
   do {                                                                                            \
@@ -1258,11 +1277,23 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     // ---- the 36 stream bytes of this step straight from the L1 (three word loads per lane, 44 contiguous bytes per
     // warp): 7 instructions instead of the 17 of the register window, and 36 warps per SM cover the L1 latency
     const uint32_t i1 = ip + tmis + lane, k1 = i1 >> 2, sh = (i1 & 3) * 8;
-    const uint32_t w0 = __ldg(tw + umin32(k1, tw_last)), w1 = __ldg(tw + umin32(k1 + 1, tw_last)), w2 = __ldg(tw + umin32(k1 + 2, tw_last));
+    uint32_t w0, w1, w2;
+    if constexpr (kOverRead && SNB_DEC_FASTFETCH) {
+      // nothing needs clamping: one address register, three loads with immediate offsets and the prefetch -- 9
+      // instructions instead of 21 (a per-step test for "far from the end" is if-converted: both forms would issue)
+      const uint32_t* const q = tw + k1;
+      w0 = __ldg(q); w1 = __ldg(q + 1); w2 = __ldg(q + 2);
 #if SNB_DEC_PREFETCH
-    // the stream is read once: without this every fourth step waits for a new 128-byte line to come from DRAM
-    prefetch_l1(tw + umin32(k1 + SNB_DEC_PREFETCH / 4, tw_last));
+      prefetch_l1(q + SNB_DEC_PREFETCH / 4);
 #endif
+    } else {
+      const uint32_t tw_last = (tn + tmis - 1) >> 2;   // tn >= 1 here
+      w0 = __ldg(tw + umin32(k1, tw_last)); w1 = __ldg(tw + umin32(k1 + 1, tw_last)); w2 = __ldg(tw + umin32(k1 + 2, tw_last));
+#if SNB_DEC_PREFETCH
+      // the stream is read once: without this every fourth step waits for a new 128-byte line to come from DRAM
+      prefetch_l1(tw + umin32(k1 + SNB_DEC_PREFETCH / 4, tw_last));
+#endif
+    }
 #endif
     const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
     const uint32_t pos = ip + lane;
@@ -1270,7 +1301,12 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     const uint32_t avail = inb ? tn - pos : 0;
     const uint32_t t = lo & 0xff, v4 = __funnelshift_r(lo, hi, 8);   // bytes past `avail` are never used when !bad
     // ---- decode "a tag starting at my byte" (decoder.nim:39-109): L output bytes, `size` stream bytes
+#if SNB_DEC_LUT32 && !defined(SNB_EMULATE)
+    uint2 te;   // 32-bit shared address kept in a register: the generic form rebuilds the window base in every step (S2UR + 3 uniform ops)
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(te.x), "=r"(te.y) : "r"(lut_s + t * 8u));
+#else
     const uint2 te = lut[t];
+#endif
     const bool lit = te.y == 0;
     const uint32_t kind = lit ? 0u : 1u;                         // literal / copy is all the rest of the step needs
     uint32_t L = te.x & 0xffu, size = (te.x >> 8) & 0xffu, hdr = 1;
@@ -1298,11 +1334,19 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     const bool is_tag = inb && ((R >> lane) & 1u);
     const uint32_t val = (is_tag && !bad) ? L : 0;
     uint32_t incl = val;
+#if SNB_DEC_SHFLPRED && !defined(SNB_EMULATE)
+    // shfl.up reports "source lane in range" as a predicate: one predicated add per round instead of a compare, a
+    // select and an add (the five lane >= d predicates do not stay in predicate registers across the step)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+      asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }" : "+r"(incl) : "r"(d));
+#else
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       uint32_t u = __shfl_up_sync(kFull, incl, d);
       if (lane >= (uint32_t)d) incl += u;
     }
+#endif
     const uint32_t my_op = op + (incl - val);
     bool e = is_tag && bad;
     if (is_tag && !bad) {
@@ -1408,6 +1452,12 @@ __global__ void __launch_bounds__(SNB_DEC_THREADS, SNB_DEC_MINB) decompress_kern
   if (a.verify) crc_stage_tables(&t, g);
   stage_tag_lut(lut);
   uint32_t lane = threadIdx.x & 31;
+  uint64_t in_hi;   // a readable bound of the input buffer: the end of its first or last chunk, whichever is higher
+  {
+    const Chunk c0 = a.chunks[0], cl = a.chunks[a.count - 1];
+    const uint64_t e0 = c0.in_off + c0.in_len, el = cl.in_off + cl.in_len;
+    in_hi = e0 > el ? e0 : el;
+  }
   for (;;) {
     uint32_t job = 0;
     if (lane == 0) job = atomicAdd(a.counter, 1u);
@@ -1420,10 +1470,12 @@ __global__ void __launch_bounds__(SNB_DEC_THREADS, SNB_DEC_MINB) decompress_kern
     int32_t st = kOk;
     uint32_t w = 0;
     const uint8_t* produced = out;
-    if (c.kind == kKindCompressed) {
-      st = decompress_warp(in, c.in_len, out, c.out_cap, &w, lane, lut);
-    } else if (c.kind == kKindRawBlock) {
-      st = decompress_warp(in, c.in_len, out, c.out_cap, &w, lane, lut, true);
+    if (c.kind == kKindCompressed || c.kind == kKindRawBlock) {
+      // every chunk's payload lies in one buffer: what the highest chunk covers is readable, so all chunks but the
+      // ones within kDecOverRead bytes of that end may over-read their stream
+      const bool bare = c.kind == kKindRawBlock;
+      if (c.in_off + c.in_len + kDecOverRead <= in_hi) st = decompress_warp<true>(in, c.in_len, out, c.out_cap, &w, lane, lut, bare);
+      else st = decompress_warp<false>(in, c.in_len, out, c.out_cap, &w, lane, lut, bare);
     } else if (c.kind == kKindStored) {
       warp_copy(out, in, c.in_len, lane);
       w = c.in_len;
