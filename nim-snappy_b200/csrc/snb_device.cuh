@@ -1243,11 +1243,12 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
       const uint32_t b_[4] = {__funnelshift_r(px0, px1, pssh), __funnelshift_r(px1, px2, pssh),   \
                               __funnelshift_r(px2, px3, pssh), __funnelshift_r(px3, px4, pssh)};  \
       uint8_t* d_ = out + pdst;                                                                   \
+      const uint32_t m_ = 0xffffffffu >> (32u - pL);   /* bit tests compile to one R2P per 7 predicates */ \
       _Pragma("unroll") for (uint32_t i_ = 0; i_ < 8; i_++)                                       \
-        if (i_ < pL) d_[i_] = (uint8_t)(b_[i_ >> 2] >> (8 * (i_ & 3)));                           \
+        if ((m_ >> i_) & 1u) d_[i_] = (uint8_t)(b_[i_ >> 2] >> (8 * (i_ & 3)));                   \
       if (pL > 8) {                                                                               \
         _Pragma("unroll") for (uint32_t i_ = 8; i_ < 16; i_++)                                    \
-          if (i_ < pL) d_[i_] = (uint8_t)(b_[i_ >> 2] >> (8 * (i_ & 3)));                         \
+          if ((m_ >> i_) & 1u) d_[i_] = (uint8_t)(b_[i_ >> 2] >> (8 * (i_ & 3)));                 \
       }                                                                                           \
       pL = 0;                                                                                     \
     }                                                                                             \
@@ -1366,7 +1367,7 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     if (is_tag && indep && L <= 16) {
       const uint8_t* s = kind == 0 ? tags + pos + hdr : out + my_op - off;
       const uint32_t sa = (uint32_t)((uintptr_t)s & 3);
-      const uint32_t* sw = (const uint32_t*)(s - sa);
+      const uint32_t* sw = (const uint32_t*)((uintptr_t)s & ~(uintptr_t)3);
       const uint32_t nw = (L + sa + 3) >> 2;                     // 1..5 words hold the L source bytes
       px0 = sw[0]; px1 = nw > 1 ? sw[1] : 0u; px2 = nw > 2 ? sw[2] : 0u;
       px3 = nw > 3 ? sw[3] : 0u; px4 = nw > 4 ? sw[4] : 0u;
