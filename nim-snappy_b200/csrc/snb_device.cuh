@@ -95,6 +95,16 @@ __device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 #endif
+// 32-bit load from a pointer the compiler only knows as generic (a select between the stream and the output)
+#ifdef SNB_EMULATE
+__device__ __forceinline__ uint32_t ld_global32(const uint32_t* p) { return *p; }
+#else
+__device__ __forceinline__ uint32_t ld_global32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+#endif
 #ifndef SNB_CRC_AFTER
 #define SNB_CRC_AFTER 0
 #endif
@@ -1374,16 +1384,17 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     // output (literals always are); independent short elements are copied by their own lane with
     // wide loads (stored one step later), long ones by the whole warp, dependent ones in order.
     if (is_tag && indep && L <= 16) {
-      const uint8_t* s = kind == 0 ? tags + pos + hdr : out + my_op - off;
+      const uint8_t* s = (kind == 0 ? tags : out) + (kind == 0 ? pos + hdr : my_op - off);
       const uint32_t sa = (uint32_t)((uintptr_t)s & 3);
       const uint32_t* sw = (const uint32_t*)((uintptr_t)s & ~(uintptr_t)3);
       const uint32_t nw = (L + sa + 3) >> 2;                     // 1..5 words hold the L source bytes
       // words past the element keep whatever they held: the flush never stores a byte that comes from them
-      px0 = sw[0];
-      if (nw > 1) px1 = sw[1];
-      if (nw > 2) px2 = sw[2];
-      if (nw > 3) px3 = sw[3];
-      if (nw > 4) px4 = sw[4];
+      const uint32_t wm = 0xffffffffu >> (32u - nw);   // bit tests: predicated loads instead of a ladder of branches
+      px0 = ld_global32(sw);
+      if (wm & 2u) px1 = ld_global32(sw + 1);
+      if (wm & 4u) px2 = ld_global32(sw + 2);
+      if (wm & 8u) px3 = ld_global32(sw + 3);
+      if (wm & 16u) px4 = ld_global32(sw + 4);
       pssh = sa * 8; pL = L; pdst = my_op;
     }
     while (lmask) {
