@@ -1359,11 +1359,9 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
     }
 #endif
     const uint32_t my_op = op + (incl - val);
-    bool e = is_tag && bad;
-    if (is_tag && !bad) {
-      if (kind != 0 && (off == 0 || off > my_op)) e = true;    // :112-113
-      if (my_op > lim || lim - my_op < L) e = true;            // :77, :127
-    }
+    // branch-free (plain & and |: predicate logic instead of a divergent region); for a bad tag L and off are never used
+    const bool e = is_tag & (bad | ((kind != 0) & ((off == 0) | (off > my_op)))    // :112-113
+                             | (my_op > lim) | (lim - my_op < L));                // :77, :127
     // every vote / shuffle of the step follows at once (the malformed-stream exit after them): each divergent region
     // between two collectives costs a convergence test (UMOV + BRA.DIV)
     const uint32_t emask = __ballot_sync(kFull, e);
@@ -1458,13 +1456,16 @@ __global__ void __launch_bounds__(1024) decode_order_kernel(const Chunk* chunks,
   for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) order[atomicAdd(&hist[257u - umin32(chunks[i].in_len >> 8, 257u)], 1u)] = i;
 }
 
-// 6 warps x 6 CTAs = 36 warps per SM at 56 registers (no spills); measured on B200 (1 GiB text / mixed):
-// 256x4 154 / 214 GB/s, 128x9 154 / 221, 192x6 157 / 226, 128x10 148 / 216 (spills), 256x5 155 / 218 (spills)
+// Launch geometry, measured on B200 (1 GiB text).  Round 1 (244 instructions per step, issue slots 72 % busy): 36 warps per SM
+// at 56 registers were as good as anything (256x4 154 GB/s, 128x9 154, 192x6 157, 128x10 148, 256x5 155).  After the round-2f
+// instruction diet (200 per step, 67 % busy) occupancy pays again: 256x5 = 40 warps per SM at 48 registers (16 bytes of
+// spill) 5.23 ms, 192x6 5.38, 160x8 5.30, 128x10 5.44 (ten CTAs' tables squeeze the L1), 320x4 5.42, 384x3 5.36, 640x2 5.54,
+// 448x3 / 672x2 (40 registers, 124 bytes of spill) 6.06 / 6.13.
 #ifndef SNB_DEC_MINB
-#define SNB_DEC_MINB 6
+#define SNB_DEC_MINB 5
 #endif
 #ifndef SNB_DEC_THREADS
-#define SNB_DEC_THREADS 192
+#define SNB_DEC_THREADS 256
 #endif
 constexpr uint32_t kDecThreads = SNB_DEC_THREADS, kDecBlocksPerSm = SNB_DEC_MINB;
 __global__ void __launch_bounds__(SNB_DEC_THREADS, SNB_DEC_MINB) decompress_kernel(DecompressArgs a, const CrcTables* g) {
