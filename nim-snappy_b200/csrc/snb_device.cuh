@@ -1244,7 +1244,9 @@ __device__ __forceinline__ int32_t decompress_warp(const uint8_t* __restrict__ i
   uint32_t pL = 0, pdst = 0, pssh = 0, px0 = 0, px1 = 0, px2 = 0, px3 = 0, px4 = 0;
 #if SNB_DEC_LUT32 && !defined(SNB_EMULATE)
   uint32_t lut_s;
-  asm volatile("mov.u32 %0, %1;" : "=r"(lut_s) : "r"((uint32_t)__cvta_generic_to_shared(lut)));   // opaque: not rematerialised in the loop
+  // through a shuffle, so that ptxas cannot rematerialise it in the loop (it sees through a plain mov, and does so when
+  // registers are tight: four uniform instructions per step again in the 48-register build)
+  lut_s = __shfl_sync(kFull, (uint32_t)__cvta_generic_to_shared(lut), 0);
 #endif
 
 #define SNB_FLUSH_SHORT()                                                                         \
