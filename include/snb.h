@@ -160,7 +160,10 @@ int snb_dev_compress_framed(const uint8_t *d_in, uint64_t n, uint8_t *d_out, uin
                             uint32_t *d_frame_lens, uint64_t *d_written, uint64_t *written, void *stream);
 
 /* Decode `count` chunks of a device-resident framed stream into d_out.  h_status[i] receives
- * the per-chunk status (0 / INVALID_INPUT / CRC_MISMATCH); synchronises the stream. */
+ * the per-chunk status (0 / INVALID_INPUT / CRC_MISMATCH); synchronises the stream.
+ * Every descriptor's (in_off, in_len) must lie inside the one buffer d_in points to: the decoder
+ * reads a chunk's stream up to 320 bytes past its end when another descriptor of the call covers
+ * those bytes (never past the highest end any descriptor names). */
 int snb_dev_uncompress_chunks(const uint8_t *d_in, const snb_chunk *h_chunks, size_t count, uint8_t *d_out,
                               int check_integrity, int32_t *h_status, void *stream);
 
