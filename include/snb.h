@@ -174,7 +174,9 @@ int snb_dev_uncompress_chunks(const uint8_t *d_in, const snb_chunk *h_chunks, si
 int snb_dev_compress_batch(const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, size_t count,
                            uint32_t max_len, uint8_t *d_out, const uint64_t *d_out_off, uint32_t *d_out_len,
                            void *stream);
-/* Batched raw-format `uncompress`.  d_status[i]: 0 / BUFFER_TOO_SMALL / INVALID_INPUT. */
+/* Batched raw-format `uncompress`.  d_status[i]: 0 / BUFFER_TOO_SMALL / INVALID_INPUT.
+ * All messages lie in the one buffer d_in points to (same bounded over-read as above: up to 320 bytes past a
+ * message, never past the higher end of the first and the last message of the call). */
 int snb_dev_uncompress_batch(const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, size_t count,
                              uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap,
                              uint32_t *d_out_len, int32_t *d_status, void *stream);
